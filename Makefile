@@ -1,0 +1,28 @@
+# Build everything in-tree (the .so files are git-ignored but travel to the GPU box).
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
+PKG       := slam_maskrcnn_b200
+LIB       := $(PKG)/libsfm_b200.so
+CSRC      := $(PKG)/csrc/sfm_api.cu
+CHDR      := $(wildcard $(PKG)/csrc/*.cuh) include/sfm_b200.h
+
+all: $(LIB) oracle/liboracle.so driver/sfm_driver
+
+$(LIB): $(CSRC) $(CHDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)
+
+# CPU oracle (test infrastructure).  -ffp-contract=off: no FMA contraction beyond the explicit fmaf().
+oracle/liboracle.so: oracle/sfm_oracle.c
+	gcc -O2 -fPIC -shared -ffp-contract=off -mfma -fopenmp -o $@ $< -lm
+
+driver/sfm_driver: driver/kernel.cpp include/sfm_b200.hpp include/sfm_b200.h $(LIB)
+	g++ -O2 -std=c++17 -Iinclude -o $@ driver/kernel.cpp -L$(PKG) -lsfm_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lz
+
+ref:
+	python oracle/build_ref.py
+
+clean:
+	rm -f $(LIB) oracle/liboracle.so driver/sfm_driver
+
+.PHONY: all ref clean

@@ -1,0 +1,487 @@
+#!/usr/bin/env python3
+"""bench.py -- labelled TSDF integration throughput (voxel-updates/s) on B200, with roofline,
+end-to-end and CPU-baseline figures.  Contract: `python bench.py --gpus N --steps K --warmup W`
+(under torchrun for N > 1) prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json metric "voxel-updates/s (512^3, 640x480, labeled)"):
+  N=1  512^3 volume, 80-bin instance histogram, synthetic TUM-fr2-shaped 640x480 frames.
+  N>1  weak scaling: the same physical cube refined so that every GPU owns 512^3 voxels as one
+       z-slab (N=2: 512x512x1024, N=4: 1024x512x1024, N=8: 1024^3 = BASELINE config 3); rank 0
+       owns the frames and broadcasts each one over NCCL; no other data-path collective.
+A step = one frame integrated into the volume (K0 prep + K1 integrate).
+
+  value  device-timed: frames already resident in HBM (rank 0's HBM for N>1, broadcast inside the step)
+  e2e    the same metric through the C-ABI call `sfm_integrate_raw` with HOST (pinned) frame
+         buffers: H2D copies inside the timed region, U/S counters read back every step
+  roofline  K1's algorithmic bytes (16*U + 14*S + frame + pose) / K1's own CUDA-event time
+  cpu_baseline  the reference's NumPy TSDF_Python integrate (restated in oracle/tsdf_numpy.py) on a
+         bounded sample of the same workload, timed on this box's host cores
+`--impl reference` runs only that CPU arm and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAME_BYTES = 640 * 480 * 6
+POSE_BYTES = 64
+N_INSTANCES = 40
+
+
+def dims_for(n_gpus):
+    return {1: (512, 512, 512), 2: (512, 512, 1024), 4: (1024, 512, 1024), 8: (1024, 1024, 1024)}[n_gpus]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.ok = index, [], False, False
+        self.busy = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.busy, sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        busy = [s for s in self.samples if s[0]] or self.samples
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+        seen = 0
+        for _, _, r in busy:
+            seen |= r
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([s[1] for s in busy])), "sm_max_mhz": mx,
+                "reasons": [n for b, n in names.items() if seen & b], "samples_under_load": len(busy)}
+
+
+def make_frames(n_pool, dims):
+    """A pool of distinct synthetic frames (cycled over the steps) + the volume placement."""
+    from slam_maskrcnn_b200 import synth
+    sc = synth.SynthScene(n_instances=N_INSTANCES, seed=0, yaw_step_deg=2.0, permute=True)
+    K = synth.intrinsic_matrix()
+    Kinv = synth.intrinsic_inverse(K)
+    f0 = sc.frame(0)
+    md = synth.mean_depth(f0["depth"])
+    start, end, voxel, miu = synth.place_volume(f0["depth"], Kinv, md, dims)
+    frames = [sc.frame(1 + i) for i in range(n_pool)]
+    return sc, K, Kinv, (start, end, voxel, miu), frames
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's NumPy integrate on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_numpy_sample(dims, frames, place, n_frames, x_planes, reps=1):
+    """Integrate `n_frames` frames into `x_planes` evenly spaced x-planes of a dims[0]^3 volume with the
+    NumPy restatement.  Returns (voxel-updates, seconds).  The NumPy code is cubic-volume only
+    (tsdf.py:21), so the sample is taken from the dims[0]^3 cube of the same physical box."""
+    from oracle.tsdf_numpy import NumpyTSDF
+    from slam_maskrcnn_b200 import synth
+    D = dims[0]
+    start, end, voxel, miu = place
+    best = None
+    for _ in range(reps):
+        t_total, vox = 0.0, 0
+        for x0 in np.linspace(0, D - 1, x_planes).astype(int):
+            # a one-plane-thick volume placed at that x: the same arithmetic per voxel, bounded memory
+            tsdf = NumpyTSDF((synth.FX, synth.FY, synth.CX, synth.CY), vol_dim=D)
+            tsdf.vol_start = np.asarray(start, np.float64)
+            tsdf.vol_end = np.asarray(end, np.float64)
+            tsdf.voxel = (tsdf.vol_end - tsdf.vol_start) / (D - 1)
+            tsdf.mu = 5 * tsdf.voxel[0]
+            n = D * D
+            tsdf.tsdf_diff = np.ones(n, np.float32) * np.float32(tsdf.mu)
+            tsdf.tsdf_wt = np.zeros(n, np.int32)
+            tsdf.tsdf_color = np.zeros((n, 3), np.int32)
+            for fr in frames[:n_frames]:
+                t0 = time.perf_counter()
+                integrate_plane(tsdf, fr["depth"], fr["color"], fr["extrinsic"].astype(np.float64), int(x0))
+                t_total += time.perf_counter() - t0
+                vox += n
+        if best is None or t_total < best[1]:
+            best = (vox, t_total)
+    return best
+
+
+def integrate_plane(tsdf, depth, color, E, x0):
+    """tsdf.py:78-120 on the x-plane x0 (state arrays hold just that plane)."""
+    D = tsdf.vol_dim
+    # re-base the flat indices of NumpyTSDF.integrate onto the plane-sized state
+    flattened_idx = np.arange(x0 * D * D, (x0 + 1) * D * D)
+    x_idx = flattened_idx // (D * D)
+    y_idx = flattened_idx // D - x_idx * D
+    z_idx = flattened_idx % D
+    pos_inhomo = tsdf.vol_start + np.stack([x_idx, y_idx, z_idx], axis=-1) * tsdf.voxel
+    pos_homo = np.concatenate([pos_inhomo, np.ones([pos_inhomo.shape[0], 1])], axis=-1)
+    proj = np.dot(E, pos_homo.transpose())
+    pixel = np.dot(tsdf.intrinsic, proj)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pixel /= pixel[2, :]
+    pixel = pixel.transpose()
+    with np.errstate(invalid="ignore"):
+        x = np.nan_to_num(pixel[:, 0], nan=-1.0, posinf=-1.0, neginf=-1.0).astype(int)
+        y = np.nan_to_num(pixel[:, 1], nan=-1.0, posinf=-1.0, neginf=-1.0).astype(int)
+    mask = (x >= 0) & (x <= color.shape[1] - 1) & (y >= 0) & (y <= color.shape[0] - 1)
+    idx = (np.minimum(np.maximum(y, 0), color.shape[0] - 1), np.minimum(np.maximum(x, 0), color.shape[1] - 1))
+    diff = depth[idx] / 5000 - proj[2, :]
+    mask &= (depth[idx] > 0)
+    diff = np.maximum(np.minimum(diff, tsdf.mu), -tsdf.mu) / tsdf.mu
+    mask &= diff > -1
+    weight = 1
+    wt, col, dif = tsdf.tsdf_wt, tsdf.tsdf_color, tsdf.tsdf_diff
+    weight_mask = wt > 0
+    a = mask & weight_mask
+    dif[a] = (dif[a] * wt[a] + weight * diff[a]) / (wt[a] + weight)
+    col[a] = (col[a] * np.expand_dims(wt[a], -1) + weight * color[idx][a]) / np.expand_dims(wt[a] + weight, -1)
+    b = mask & ~weight_mask
+    dif[b] = weight * diff[b]
+    col[b] = weight * color[idx][b]
+    wt[mask] = wt[mask] + weight
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return 1
+
+
+def cpu_c_oracle_sample(dims, bins, frames, place, K, n_frames, z_planes):
+    """The C restatement of tsdf_kernel (labelled, OpenMP over all host cores) on a z-slab sample."""
+    from oracle import binding as ob
+    start, end, voxel, miu = place
+    D = (dims[0], dims[1], z_planes)
+    # a thin slab in the middle of the volume: shift the z origin so the slab sits at mid depth
+    z_mid = dims[2] // 2
+    st = np.array(start, np.float32).copy()
+    st[2] = np.float32(start[2] + voxel[2] * z_mid)
+    vol = ob.CpuVolume(D, bins, st, end, voxel, miu)
+    t_total = 0.0
+    for fr in frames[:n_frames]:
+        t0 = time.perf_counter()
+        vol.integrate(K, fr["depth"], fr["color"], fr["gt"], fr["extrinsic"], 640, 480)
+        t_total += time.perf_counter() - t0
+    return D[0] * D[1] * D[2] * n_frames, t_total
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims = dims_for(args.gpus)
+    sc, K, Kinv, place, frames = make_frames(4, dims)
+    x_planes = 4
+    # warm-up
+    for _ in range(max(args.warmup, 0)):
+        cpu_numpy_sample(dims, frames, place, 1, 1)
+    t_all, v_all = 0.0, 0
+    for s in range(args.steps):
+        vox, sec = cpu_numpy_sample(dims, frames[s % len(frames):] + frames[:s % len(frames)], place, 1, x_planes)
+        t_all += sec
+        v_all += vox
+    value = v_all / t_all
+    sample = (f"per step: 1 frame (640x480) into {x_planes} evenly spaced x-planes of the {dims[0]}^3 cube "
+              f"({x_planes * dims[0] * dims[0]} voxels), NumPy float64, labels off as in the reference code")
+    line = {
+        "impl": "reference", "metric": "voxel-updates/s", "value": value, "unit": "voxel-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus, dims), "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxel-updates/s", "cores": blas_threads(), "kind": "port",
+                         "sample": sample + f"; host has {os.cpu_count()} cores, only the 4x4 np.dot is multi-threaded"},
+        "e2e": {"value": value, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(n_gpus, dims):
+    return (f"labelled TSDF integrate, {dims[0]}x{dims[1]}x{dims[2]} voxels ({'one GPU' if n_gpus == 1 else f'{n_gpus} z-slabs'}), "
+            f"80-bin instance histogram, synthetic TUM-fr2-shaped 640x480 depth+BGR+label frames")
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from slam_maskrcnn_b200 import Volume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    assert world == n_gpus or world == 1 and n_gpus == 1, f"launched with WORLD_SIZE={world} but --gpus {n_gpus}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the CUDA path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    dims = tuple(args.dims) if args.dims else dims_for(n_gpus)
+    bins = args.bins
+    nz = dims[2] // world
+    slab = (rank * nz, nz)
+    K_steps, W_steps = args.steps, max(args.warmup, 3)
+    n_pool = min(args.pool, K_steps + W_steps)
+    sc, K, Kinv, place, frames = make_frames(n_pool, dims)
+    vol = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=slab,
+                 flags=args.flags)
+    stream = torch.cuda.current_stream()
+    vol.set_stream(stream.cuda_stream)
+    vol.set_bounds(*place)
+    vol.synchronize()
+
+    # frames: packed [depth | colour | mask | pose] byte buffers, pinned on the host and resident in HBM
+    npx = 640 * 480
+    packed_host = []
+    for fr in frames:
+        buf = torch.empty(FRAME_BYTES + POSE_BYTES, dtype=torch.uint8).pin_memory()
+        b = buf.numpy()
+        b[:npx * 2] = fr["depth"].reshape(-1).view(np.uint8)
+        b[npx * 2:npx * 5] = fr["color"].reshape(-1)
+        b[npx * 5:npx * 6] = fr["gt"].reshape(-1)
+        b[npx * 6:] = fr["extrinsic"].astype(np.float32).reshape(-1).view(np.uint8)
+        packed_host.append(buf)
+    poses = [fr["extrinsic"].astype(np.float32) for fr in frames]
+    if rank == 0 or world == 1:
+        packed_dev = [b.cuda(non_blocking=True) for b in packed_host]
+    else:
+        packed_dev = None
+    bcast_buf = [torch.empty(FRAME_BYTES + POSE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        """One step with the frame resident in (rank 0's) HBM."""
+        j = i % n_pool
+        if world > 1:
+            buf = bcast_buf[i & 1]
+            if rank == 0:
+                buf.copy_(packed_dev[j], non_blocking=True)
+            dist.broadcast(buf, src=0)
+        else:
+            buf = packed_dev[j]
+        p = buf.data_ptr()
+        vol.integrate_dev(p, p + npx * 2, p + npx * 5, poses[j])
+
+    def step_e2e(i):
+        """One step through the host-buffer C-ABI call; U/S counters read back."""
+        j = i % n_pool
+        if world > 1:
+            buf = bcast_buf[i & 1]
+            if rank == 0:
+                buf.copy_(packed_host[j], non_blocking=True)
+            dist.broadcast(buf, src=0)
+            p = buf.data_ptr()
+            vol.integrate_dev(p, p + npx * 2, p + npx * 5, poses[j])
+        else:
+            b = packed_host[j].numpy()
+            vol.integrate_raw(b[:npx * 2].view(np.uint16), b[npx * 2:npx * 5], b[npx * 5:npx * 6], poses[j])
+        return vol.frame_stats()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- device-timed region ---------------------------------------------------------------
+    for i in range(W_steps):
+        step_device(i)
+    vol.frame_stats()
+    barrier()
+    launches0 = vol.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.busy = True
+    ev0.record()
+    for i in range(K_steps):
+        step_device(W_steps + i)
+    ev1.record()
+    barrier()
+    sampler.busy = False
+    t_dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = vol.launch_count() - launches0
+    U, S = vol.frame_stats()
+    k1_ms = vol.integrate_times(min(K_steps, 2048)).astype(np.float64)
+    k1_ms_max = max_over_ranks(float(k1_ms.mean()))
+
+    # ---- end-to-end region (host buffers, H2D + result D2H every step) ----------------------
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    sampler.busy = True
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(K_steps):
+        step_e2e(W_steps + i)
+    ev1.record()
+    barrier()
+    t_e2e_wall = time.perf_counter() - t0
+    sampler.busy = False
+    t_e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0))
+
+    # ---- labelled fusion with duplicate-instance merge through sfm_fuse_frame (N=1 only) -----
+    fused = None
+    if world == 1 and bins > 0 and not args.no_merge:
+        try:
+            masks = [fr["mask"].copy() for fr in frames]
+            b0 = vol.launch_count()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nf = min(K_steps, n_pool)
+            for i in range(nf):
+                fr = frames[i]
+                vol.fuse_frame(fr["depth"], fr["color"], masks[i], fr["extrinsic"])
+            vol.synchronize()
+            dt = time.perf_counter() - t0
+            fused = {"frames": nf, "ms_per_frame": 1e3 * dt / nf, "voxel_updates_per_s": int(np.prod(dims)) * nf / dt,
+                     "num_objs": int(vol.info().num_objs), "launches": vol.launch_count() - b0,
+                     "what": "sfm_fuse_frame: H2D + back-project/fold (K2) + host decision + relabel + K0 + K1, pageable host buffers"}
+        except Exception as e:  # reported, never hidden
+            fused = {"error": str(e)}
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    n_vox_rank = dims[0] * dims[1] * nz
+    n_vox_total = n_vox_rank * world
+    value = n_vox_total * K_steps / (t_dev_ms * 1e-3)
+    e2e_value = n_vox_total * K_steps / (t_e2e_ms * 1e-3)
+    # roofline of the dominant kernel (K1) on this rank: algorithmic bytes / K1 event time
+    n_timed = len(k1_ms)
+    alg_bytes = 16.0 * U + 14.0 * S + (FRAME_BYTES + POSE_BYTES) * K_steps
+    alg_per_launch = alg_bytes / K_steps
+    peak, peak_src = measured_peaks()
+    achieved = alg_per_launch / (k1_ms.mean() * 1e-3) / 1e9
+    U_all, S_all = sum_over_ranks(U), sum_over_ranks(S)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        vox, sec = cpu_numpy_sample(dims, frames, place, 2, 6, reps=2)
+        sample = (f"2 frames (640x480) into 6 evenly spaced x-planes of the {dims[0]}^3 cube ({vox} voxel-updates, "
+                  f"best of 2), NumPy float64 restatement of TSDF_Python/tsdf.py:78-120, labels off as in the reference")
+        cpu_base = {"value": vox / sec, "unit": "voxel-updates/s", "cores": blas_threads(), "kind": "port", "sample": sample,
+                    "host_cores": os.cpu_count(), "seconds": sec}
+        try:
+            vox_c, sec_c = cpu_c_oracle_sample(dims, bins, frames, place, K, 2, 16)
+            cpu_base["c_oracle_openmp"] = {"value": vox_c / sec_c, "unit": "voxel-updates/s", "cores": os.cpu_count(),
+                                           "sample": f"2 labelled frames into a {dims[0]}x{dims[1]}x16 mid-depth slab, C restatement of tsdf_kernel"}
+        except Exception as e:
+            cpu_base["c_oracle_openmp"] = {"error": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "voxel-updates/s", "value": value, "unit": "voxel-updates/s", "n_gpus": n_gpus,
+            "steps": K_steps, "warmup": W_steps, "ms_per_step": t_dev_ms / K_steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n_gpus, dims), "dims": list(dims), "bins": bins,
+                       "voxels_per_gpu": n_vox_rank, "frame_pool": n_pool,
+                       "l2": "no flush: each step reads and writes ~0.25 GB of voxel planes out of a >40 GB working set (> 126 MB L2)",
+                       "frames_resident": "HBM (rank 0), NCCL broadcast inside each step" if world > 1 else "HBM"},
+            "touched_voxel_updates_per_s": U_all / (t_dev_ms * 1e-3),
+            "U_per_step": U_all / K_steps, "S_per_step": S_all / K_steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "integrate_kernel<4,true,true> (K1)",
+                         "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_avg": float(k1_ms.mean()),
+                         "kernel_ms_avg_max_rank": k1_ms_max, "launches_timed": n_timed,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "e2e": {"value": e2e_value, "unit": "voxel-updates/s", "h2d_bytes_per_step": FRAME_BYTES,
+                    "d2h_bytes_per_step": 4096, "ms_per_step": t_e2e_ms / K_steps, "wall_ms_per_step": 1e3 * t_e2e_wall / K_steps,
+                    "api": "sfm_integrate_raw(host pinned depth,colour,mask, pose) + sfm_frame_stats" if world == 1 else
+                           "pinned host frame -> H2D on rank 0 -> ncclBroadcast -> sfm_integrate_dev + sfm_frame_stats"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "fused_merge_path": fused,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": "voxel-updates/s", "cores": 0, "kind": "port",
+                                    "sample": "timed at N=1 only"}
+        print(json.dumps(line))
+    vol.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dims", type=int, nargs=3, default=None)
+    ap.add_argument("--bins", type=int, default=80)
+    ap.add_argument("--pool", type=int, default=12, help="distinct synthetic frames cycled over the steps")
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-merge", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

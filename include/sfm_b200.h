@@ -1,0 +1,205 @@
+/* sfm_b200.h -- C-ABI of the B200-native TSDF fusion + ray-cast path.
+ *
+ * Drop-in boundary for the hot path of qq456cvb/SLAM-MaskRCNN's src/SfM_CUDA.  The reference
+ * has no FFI: its boundary is two C++ classes with OpenCV types (`class TSDF`, tsdf.cuh:7-67;
+ * `class Viewer`, viewer.cuh:4-17) called from kernel.cpp:37-111.  Every entry point below
+ * names the reference interface it replaces.  include/sfm_b200.hpp re-creates `TSDF` / `Viewer`
+ * with the reference's method names on top of this header so a kernel.cpp-style main compiles
+ * against it.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Return 0 on success, a negative
+ * sfm_status otherwise (sfm_last_error() gives the text; the reference throws std::string after
+ * cudaGetLastError, tsdf.cu:497-503, viewer.cu:169-175).  Host buffers are borrowed for the
+ * duration of the call only.  One handle = one volume (or one z-slab of it) on one GPU, one
+ * serialised command stream; not thread-safe per handle (neither is the reference).
+ *
+ * Layouts at the boundary are the reference's (tsdf.cu:55,59,61):
+ *   voxel index  v = (x*Dy + y)*Dz + z            (z fastest)
+ *   SDF f32[v], weight i32[v], colour u8[v*3+c], histogram u32[v*bins + label]
+ *   depth u16[H][W] (metres*5000, 0 = invalid), colour u8[H][W][3] (BGR as loaded), mask u8[H][W]
+ *   all 4x4 matrices row-major f32[16].
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfm_volume sfm_volume;
+
+typedef enum {
+	SFM_OK = 0,
+	SFM_ERR_INVALID = -1,  /* bad argument / state (e.g. label >= bins, not initialised) */
+	SFM_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed                  */
+	SFM_ERR_NOMEM = -3,    /* device or host allocation failed                             */
+	SFM_ERR_NODEVICE = -4  /* no usable sm_100 device (there is NO CPU fallback)           */
+} sfm_status;
+
+typedef enum {
+	SFM_PLANE_SDF = 0,    /* f32, tsdf_diff_d  (tsdf.cuh:24) */
+	SFM_PLANE_WEIGHT = 1, /* i32, tsdf_wt_d    (tsdf.cuh:27) */
+	SFM_PLANE_COLOR = 2,  /* u8x3, tsdf_color_d (tsdf.cuh:25) */
+	SFM_PLANE_HIST = 3    /* u32 x bins, tsdf_cnt_d (tsdf.cuh:26) */
+} sfm_plane;
+
+enum {
+	SFM_FLAG_NO_CULL = 1,      /* visit every voxel (disables exact brick culling; same results) */
+	SFM_FLAG_NO_TMA = 2,       /* read frame images through the read-only path instead of TMA-staged tiles */
+	SFM_FLAG_SYNC_EVERY_CALL = 4 /* cudaStreamSynchronize before returning from every call        */
+};
+
+/* Creation parameters.  Defaults (sfm_desc_default) are the reference's hard-coded values. */
+typedef struct {
+	int32_t dims[3];        /* vol_dim_, tsdf.cuh:52 (reference: 256^3 fixed)                 */
+	int32_t bins;           /* MAX_OBJECTS, tsdf.cuh:4 (reference: 32); 0 = labels off        */
+	int32_t width, height;  /* frame size (reference: taken from the first depth frame)        */
+	float K[16];            /* intrinsic_, tsdf.cu:143-146: eye(4) with fx,fy,cx,cy            */
+	float Kinv[16];         /* intrinsic_inv_, tsdf.cu:147; all-zero => library inverts K      */
+	float prior_err_rate;   /* Configuration::prior_mrcnn_err_rate = 0.05, configuration.h:8   */
+	float duplicate_thresh; /* Configuration::duplicate_thresh = 0.5, configuration.h:9; the
+	                           reference declares and never reads it -- carried, unused        */
+	float presence_thresh;  /* 0.3f, tsdf.cu:128                                               */
+	float accept_factor;    /* 3 (x prior), tsdf.cu:349                                        */
+	float depth_scale;      /* 5000.f, tsdf.cu:49                                              */
+	float trunc_voxels;     /* 5 (miu = 5*voxel.x), tsdf.cu:199                                */
+	float near_gate;        /* 0.99f, tsdf.cu:57                                               */
+	int32_t device;         /* CUDA device ordinal                                             */
+	int32_t slab_z0;        /* first global z plane stored by this handle                      */
+	int32_t slab_nz;        /* number of z planes stored (0 => all of dims[2])                 */
+	int32_t flags;          /* SFM_FLAG_*                                                      */
+	int32_t reserved[8];
+} sfm_desc;
+
+typedef struct {
+	int32_t dims[3];
+	int32_t bins;
+	int32_t width, height;
+	int32_t slab_z0, slab_nz;
+	float vol_start[3], vol_end[3], voxel[3]; /* vol_start_/vol_end_/vol_res_, tsdf.cuh:54-55 */
+	float miu;                                /* miu_, tsdf.cuh:51                             */
+	float mean_depth;                         /* mean_depth_, tsdf.cuh:11                      */
+	uint32_t n_obs;                           /* n_obs_, tsdf.cuh:46                           */
+	int32_t num_objs;                         /* num_objs, tsdf.cuh:61                         */
+	int32_t initialised;                      /* init_, tsdf.cuh:60                            */
+	int32_t reserved[8];
+} sfm_info;
+
+/* Result of the last duplicate-instance merge (TSDF::filter_overlaps, tsdf.cu:304-416). */
+typedef struct {
+	int32_t max_obj_now;    /* max(mask)+1 of the incoming frame, tsdf.cu:305-307              */
+	int32_t num_objs;       /* after the merge                                                 */
+	int32_t assign[256];    /* current-frame label m -> global id written into the mask        */
+	float best_prob[256];   /* max_j exp(A[m][j]/C[m][j]), tsdf.cu:340-348                     */
+	float margin;           /* min distance of any decision from flipping (threshold or rival) */
+} sfm_merge_report;
+
+void sfm_desc_default(sfm_desc *d);
+const char *sfm_last_error(void);
+const char *sfm_version(void);
+
+/* TSDF::TSDF(cv::Scalar intrinsics) (tsdf.cu:137-150) + init_cuda_vars (tsdf.cu:230-280). */
+int sfm_create(const sfm_desc *desc, sfm_volume **out);
+/* TSDF::~TSDF / free_cuda_vars (tsdf.cu:152-168, 282-302). */
+void sfm_destroy(sfm_volume *v);
+
+/* Volume placement of the first parse_frame call (tsdf.cu:173-212): bbox of depth != 0,
+ * corners through Kinv scaled by mean_depth, cube of half the XY diagonal, voxel =
+ * (end-start)/(dim-1), miu = trunc_voxels*voxel.x, SDF := miu, other planes := 0, n_obs := 0,
+ * init_extrinsic_inv := extrinsic^-1.  The frame itself is NOT integrated (tsdf.cu:213). */
+int sfm_init_from_frame(sfm_volume *v, const uint16_t *depth, const float *extrinsic16, float mean_depth);
+/* Explicit placement (what the parity tests use so both sides get identical bits). */
+int sfm_set_bounds(sfm_volume *v, const float *vol_start3, const float *vol_end3, const float *voxel3, float miu);
+
+/* TSDF::parse_frame (tsdf.cu:171-228): first call = sfm_init_from_frame; later calls =
+ * extrinsic2init = extrinsic * init_extrinsic^-1, then launch_kernel (tsdf.cu:418-504):
+ * back-project + duplicate-instance merge (relabels `mask` IN PLACE) when n_obs > 0, else
+ * num_objs = max(mask)+1; integrate; n_obs++. */
+int sfm_parse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
+	const float *extrinsic16, float mean_depth);
+/* Same as the non-first branch of parse_frame with extrinsic2init given directly. */
+int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
+	const float *extrinsic2init16);
+
+/* tsdf_kernel only (tsdf.cu:18-70, launch tsdf.cu:472-488): parity hook, host frame buffers. */
+int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask,
+	const float *extrinsic2init16);
+/* Same with frame buffers already resident in device memory (multi-GPU: after the NCCL broadcast). */
+int sfm_integrate_dev(sfm_volume *v, const void *d_depth, const void *d_color, const void *d_mask,
+	const float *extrinsic2init16);
+
+/* back_proj_kernel (tsdf.cu:72-135, launch 441-455), materialised: probs f32[H*W*bins],
+ * box_mask u8[H*W*bins] on the HOST (parity hook; the fused path never builds these).
+ * t_out f32[H*W] (refined hit t, 0 = no hit) and flags_out u8[H*W] (bit0: a trilinear tap was
+ * clamped to the volume, i.e. the reference read out of bounds there) are optional. */
+int sfm_backproject(sfm_volume *v, const float *extrinsic2init16, float *probs, uint8_t *box_mask,
+	float *t_out, uint8_t *flags_out);
+/* Fused back-project + overlap fold: the tables of filter_overlaps (tsdf.cu:309-334) without
+ * materialising probs.  A f64[bins*bins] (sum of log terms), C u32[bins*bins]. */
+int sfm_overlap_tables(sfm_volume *v, const float *extrinsic2init16, const uint8_t *mask,
+	double *A, uint32_t *C);
+/* The decision + relabel half of filter_overlaps (tsdf.cu:335-389) on given tables. */
+int sfm_merge_decide(sfm_volume *v, const double *A, const uint32_t *C, uint8_t *mask_inout,
+	sfm_merge_report *report);
+int sfm_last_merge(sfm_volume *v, sfm_merge_report *report);
+
+/* Planes in the reference layout / dtypes (the getters get_tsdf_diff/color/cnt, tsdf.cu:506-516,
+ * return stale host mirrors in the reference; these copy the live device planes).
+ * For a slab handle the region is the slab's z range: [Dx][Dy][slab_nz]. */
+int sfm_download(sfm_volume *v, int plane, void *dst, size_t bytes);
+int sfm_upload(sfm_volume *v, int plane, const void *src, size_t bytes);
+size_t sfm_plane_bytes(sfm_volume *v, int plane);
+/* The reference exposes its device pointers as public members (tsdf.cuh:24-43). */
+void *sfm_plane_device_ptr(sfm_volume *v, int plane);
+
+/* show_tsdf_kernel (viewer.cu:17-86, launch 152-166).  bgr u8[h*w*3] host; t_opt f32[h*w],
+ * label_opt u8[h*w] optional. */
+int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h,
+	uint8_t *bgr, float *t_opt, uint8_t *label_opt);
+/* Per-ray flags of the last sfm_raycast / sfm_backproject (bit0: a trilinear tap was clamped to
+ * the volume -- the reference reads out of bounds on those rays). */
+int sfm_ray_flags(sfm_volume *v, uint8_t *flags, size_t n);
+/* Per-ray first-hit keys for the multi-GPU min-composite: d_keys u64[h*w] DEVICE memory,
+ * key = (float_bits(t_hit) << 32) | label, or UINT64_MAX when this slab has no hit. */
+int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, void *d_keys);
+/* key image (device) -> BGR image (host) through the palette (viewer.cu:80-83). */
+int sfm_keys_to_bgr(sfm_volume *v, const void *d_keys, int w, int h, uint8_t *bgr);
+/* Viewer::show_tsdf (viewer.cu:137-179): orbit camera matrices + ray-cast. */
+int sfm_show(sfm_volume *v, float angle, float dist, int w, int h, uint8_t *bgr);
+/* The camera matrices alone (viewer.cu:140-146). */
+void sfm_orbit_camera(const float *Kinv16, float angle, float dist, float *s2w16, float *c3);
+/* Viewer palette (viewer.cu:93-126): 16 colours repeated; index = label % 16 beyond 32. */
+void sfm_palette(uint8_t *rgb, int n);
+
+int sfm_get_info(sfm_volume *v, sfm_info *info);
+int sfm_synchronize(sfm_volume *v);
+/* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*). */
+int sfm_set_stream(sfm_volume *v, void *cuda_stream);
+/* CUDA-event timer on the handle's stream. */
+int sfm_timer_start(sfm_volume *v);
+int sfm_timer_stop(sfm_volume *v, float *ms);
+/* Number of kernel launches issued by this handle so far. */
+uint64_t sfm_launch_count(sfm_volume *v);
+/* Device time (ms) of the integrate kernel alone (K1) for the last call / the last n calls, from
+ * CUDA events the library records around each launch (ring of 2048 calls, oldest first). */
+int sfm_last_integrate_ms(sfm_volume *v, float *ms);
+int sfm_integrate_times(sfm_volume *v, float *ms, int n);
+
+/* U = voxels whose weight was incremented, S = voxels whose colour/histogram was updated, summed
+ * over the integrate calls since the previous sfm_frame_stats call: the terms of the
+ * algorithmic-bytes formula 16*U + 14*S. */
+int sfm_frame_stats(sfm_volume *v, uint64_t *U, uint64_t *S);
+
+/* Host-side helpers of the reference's driver (the "next" rows). */
+/* mean_depth (utils.cu:77-91). */
+float sfm_mean_depth(const uint16_t *depth, int n);
+/* parse_extrinsic (utils.cu:8-24): pose {tx,ty,tz,qx,qy,qz,qw} -> world->camera 4x4 f32. */
+void sfm_parse_extrinsic(const double *pose7, float *extrinsic16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

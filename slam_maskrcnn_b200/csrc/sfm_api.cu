@@ -1,0 +1,1025 @@
+// sfm_api.cu -- host side of libsfm_b200.so: the C-ABI declared in include/sfm_b200.h.
+//
+// Mirrors the per-frame sequencing of the reference's TSDF::parse_frame / launch_kernel
+// (src/SfM_CUDA/tsdf.cu:171-228, 418-504) and Viewer::show_tsdf (viewer.cu:137-179), with
+// asynchronous copies on one stream per handle, every CUDA call checked, and no CPU fallback:
+// without an sm_100 device sfm_create fails with SFM_ERR_NODEVICE.
+#include "../../include/sfm_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "k_integrate.cuh"
+#include "k_raymarch.cuh"
+
+using namespace sfm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+	g_err = msg;
+	return code;
+}
+
+#define CU(call)                                                                                     \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(e_ == cudaErrorMemoryAllocation ? SFM_ERR_NOMEM : SFM_ERR_CUDA,              \
+				std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+	} while (0)
+
+// launch check in the reference's words (tsdf.cu:497-503)
+#define LAUNCH_CHECK(v)                                                                              \
+	do {                                                                                             \
+		(v)->launches++;                                                                             \
+		cudaError_t e_ = cudaGetLastError();                                                         \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(SFM_ERR_CUDA, std::string("run_kernel launch failed\n") + cudaGetErrorString(e_)); \
+	} while (0)
+
+void mat4_mul(const float *a, const float *b, float *out) {  // float inputs, double accumulate
+	float r[16];
+	for (int i = 0; i < 4; i++)
+		for (int j = 0; j < 4; j++) {
+			double s = 0;
+			for (int k = 0; k < 4; k++) s += (double)a[i * 4 + k] * (double)b[k * 4 + j];
+			r[i * 4 + j] = (float)s;
+		}
+	memcpy(out, r, sizeof(r));
+}
+
+bool mat4_inv(const float *m, float *out) {  // Gauss-Jordan in double, partial pivoting
+	double a[4][8];
+	for (int i = 0; i < 4; i++)
+		for (int j = 0; j < 4; j++) { a[i][j] = m[i * 4 + j]; a[i][j + 4] = (i == j) ? 1.0 : 0.0; }
+	for (int c = 0; c < 4; c++) {
+		int piv = c;
+		for (int r = c + 1; r < 4; r++) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+		if (fabs(a[piv][c]) < 1e-300) return false;
+		if (piv != c) for (int j = 0; j < 8; j++) std::swap(a[piv][j], a[c][j]);
+		const double d = a[c][c];
+		for (int j = 0; j < 8; j++) a[c][j] /= d;
+		for (int r = 0; r < 4; r++) {
+			if (r == c) continue;
+			const double f = a[r][c];
+			if (f != 0.0) for (int j = 0; j < 8; j++) a[r][j] -= f * a[c][j];
+		}
+	}
+	for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[i * 4 + j] = (float)a[i][j + 4];
+	return true;
+}
+
+const uint8_t kPalette16[16 * 3] = {  // Viewer palette values, viewer.cu:93-109 (RGB triplets)
+	230, 25, 75, 60, 180, 75, 255, 225, 25, 0, 130, 200, 245, 130, 48, 145, 30, 180, 70, 240, 240, 240, 50, 230,
+	210, 245, 60, 250, 190, 190, 0, 128, 128, 230, 190, 255, 170, 110, 40, 255, 250, 200, 128, 0, 0, 170, 255, 195};
+
+struct PinnedFrame {
+	uint8_t *buf = nullptr;
+	cudaEvent_t free_ev = nullptr;  // recorded after the H2D that read this buffer
+};
+
+}  // namespace
+
+struct sfm_volume {
+	sfm_desc desc;
+	VolGeom g;
+	int bins = 0, W = 0, H = 0, TW = 0, TH = 0;
+	size_t nvox = 0;
+	Planes planes{};
+	// frame staging (device)
+	uint16_t *d_depth = nullptr;
+	uint8_t *d_rgb = nullptr, *d_mask = nullptr;
+	uint16_t *d_tilemax = nullptr;
+	unsigned long long *d_stats = nullptr;
+	uint32_t *d_err = nullptr;
+	uint8_t *d_palette = nullptr;
+	uint8_t *d_lut = nullptr;
+	// pinned staging (host), double buffered
+	PinnedFrame pin[2];
+	int pin_next = 0;
+	size_t frame_bytes = 0;
+	// ray-march scratch (device), sized lazily
+	float *d_probs = nullptr;
+	uint8_t *d_box = nullptr;
+	float *d_t = nullptr;
+	uint8_t *d_flags = nullptr;
+	uint8_t *d_bgr = nullptr, *d_label = nullptr;
+	unsigned long long *d_keys = nullptr;
+	size_t ray_px = 0;      // capacity of the per-pixel buffers
+	size_t probs_px = 0;    // capacity of probs/box
+	// merge scratch
+	uint8_t *d_fold = nullptr;
+	uint8_t *h_fold = nullptr;  // pinned mirror
+	size_t fold_bytes = 0;
+	unsigned long long *h_stats = nullptr;  // pinned
+	uint32_t *h_err = nullptr;               // pinned
+	sfm_merge_report last_merge{};
+	// state (tsdf.cuh:46-61)
+	float K[16], Kinv[16];
+	float init_extr_inv[16];
+	bool init = false;
+	uint32_t n_obs = 0;
+	int num_objs = 0;
+	float mean_depth = 0.f;
+	// execution
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+	static constexpr int kRing = 2048;  // per-call event pairs around K1 (integrate kernel only)
+	cudaEvent_t ev_k0[kRing] = {}, ev_k1[kRing] = {};
+	uint64_t n_integrate = 0;
+	uint64_t launches = 0;
+	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
+};
+
+namespace {
+
+int check_device_error(sfm_volume *v) {
+	CU(cudaMemcpyAsync(v->h_err, v->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	if (*v->h_err) {
+		CU(cudaMemsetAsync(v->d_err, 0, sizeof(uint32_t), v->stream));
+		return fail(SFM_ERR_INVALID, "a frame carried a label >= bins (histogram bin out of range); that update was skipped");
+	}
+	return SFM_OK;
+}
+
+size_t plane_elem_bytes(const sfm_volume *v, int plane) {
+	switch (plane) {
+	case SFM_PLANE_SDF: return 4;
+	case SFM_PLANE_WEIGHT: return 4;
+	case SFM_PLANE_COLOR: return 3;
+	case SFM_PLANE_HIST: return 4 * (size_t)v->bins;
+	default: return 0;
+	}
+}
+
+void *plane_ptr(const sfm_volume *v, int plane) {
+	switch (plane) {
+	case SFM_PLANE_SDF: return v->planes.sdf;
+	case SFM_PLANE_WEIGHT: return v->planes.wt;
+	case SFM_PLANE_COLOR: return v->planes.color;
+	case SFM_PLANE_HIST: return v->planes.hist;
+	default: return nullptr;
+	}
+}
+
+int reset_planes(sfm_volume *v) {
+	// tsdf.cu:242-253: SDF := miu (thrust::fill), colour / histogram / weight := 0
+	fill_f32_kernel<<<148 * 8, 256, 0, v->stream>>>(v->planes.sdf, v->nvox, v->g.miu);
+	LAUNCH_CHECK(v);
+	CU(cudaMemsetAsync(v->planes.wt, 0, v->nvox * 4, v->stream));
+	CU(cudaMemsetAsync(v->planes.color, 0, v->nvox * 3, v->stream));
+	if (v->bins > 0) CU(cudaMemsetAsync(v->planes.hist, 0, v->nvox * 4 * (size_t)v->bins, v->stream));
+	v->n_obs = 0;
+	v->num_objs = 0;
+	return SFM_OK;
+}
+
+bool is_device_or_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Upload one frame's images to the device staging buffers.  Pinned / device sources are copied
+// directly and asynchronously; pageable sources go through a double-buffered pinned bounce buffer.
+int upload_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask) {
+	const size_t npx = (size_t)v->W * v->H;
+	const size_t bd = npx * 2, bc = npx * 3, bm = npx;
+	const bool direct = (!depth || is_device_or_pinned(depth)) && (!color || is_device_or_pinned(color)) &&
+		(!mask || is_device_or_pinned(mask));
+	if (direct) {
+		if (depth) CU(cudaMemcpyAsync(v->d_depth, depth, bd, cudaMemcpyDefault, v->stream));
+		if (color) CU(cudaMemcpyAsync(v->d_rgb, color, bc, cudaMemcpyDefault, v->stream));
+		if (mask) CU(cudaMemcpyAsync(v->d_mask, mask, bm, cudaMemcpyDefault, v->stream));
+		return SFM_OK;
+	}
+	PinnedFrame &pf = v->pin[v->pin_next];
+	v->pin_next ^= 1;
+	CU(cudaEventSynchronize(pf.free_ev));
+	if (depth) { memcpy(pf.buf, depth, bd); CU(cudaMemcpyAsync(v->d_depth, pf.buf, bd, cudaMemcpyHostToDevice, v->stream)); }
+	if (color) { memcpy(pf.buf + bd, color, bc); CU(cudaMemcpyAsync(v->d_rgb, pf.buf + bd, bc, cudaMemcpyHostToDevice, v->stream)); }
+	if (mask) { memcpy(pf.buf + bd + bc, mask, bm); CU(cudaMemcpyAsync(v->d_mask, pf.buf + bd + bc, bm, cudaMemcpyHostToDevice, v->stream)); }
+	CU(cudaEventRecord(pf.free_ev, v->stream));
+	return SFM_OK;
+}
+
+FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask,
+	const float *E16)
+{
+	FrameView f{};
+	f.depth = (const uint16_t *)d_depth;
+	f.rgb = (const uint8_t *)d_rgb;
+	f.mask = (const uint8_t *)d_mask;
+	f.tilemax = v->d_tilemax;
+	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
+	memcpy(f.E, E16, 12 * sizeof(float));
+	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
+	f.depth_scale = v->desc.depth_scale;
+	f.near_gate = v->desc.near_gate;
+	float lin = 0.f, tt = 0.f;
+	for (int r = 0; r < 3; r++) {
+		lin = std::max(lin, fabsf(E16[r * 4 + 0]) + fabsf(E16[r * 4 + 1]) + fabsf(E16[r * 4 + 2]));
+		tt = std::max(tt, fabsf(E16[r * 4 + 3]));
+	}
+	const float k0 = fabsf(f.K[0]) + fabsf(f.K[1]) + fabsf(f.K[2]);
+	const float k1 = fabsf(f.K[3]) + fabsf(f.K[4]) + fabsf(f.K[5]);
+	const float k2 = fabsf(f.K[6]) + fabsf(f.K[7]) + fabsf(f.K[8]);
+	f.cull_lin = lin;
+	f.cull_t = tt;
+	f.cull_k2 = k2;
+	f.cull_slack0 = 1.f + 1e-3f * std::max(k0, k1) / std::max(k2, 1e-20f);
+	return f;
+}
+
+template <int VEC, bool LABELS>
+void launch_integrate(sfm_volume *v, const FrameView &f, bool cull, int blocks) {
+	if (cull) integrate_kernel<VEC, LABELS, true><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err);
+	else integrate_kernel<VEC, LABELS, false><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err);
+}
+
+// K0 + K1 on device-resident frame images
+int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16) {
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set (call sfm_set_bounds / sfm_init_from_frame / sfm_parse_frame first)");
+	const FrameView f = make_frame_view(v, d_depth, d_rgb, d_mask, E16);
+	const int prep_warps = v->TW * v->TH;
+	const int prep_blocks = std::max((prep_warps * 32 + 255) / 256, (2 * kStatSlots + 255) / 256);
+	prep_frame_kernel<<<prep_blocks, 256, 0, v->stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
+		v->bins, v->d_tilemax, v->d_stats, v->d_err);
+	LAUNCH_CHECK(v);
+	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL);
+	const bool vec4 = (v->g.nz % 4 == 0);
+	const int cpw = vec4 ? 4 : 1;
+	const long long groups = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw);
+	const int blocks = (int)((groups + 7) / 8);
+	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
+	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
+	if (vec4) {
+		if (v->bins > 0) launch_integrate<4, true>(v, f, cull, blocks);
+		else launch_integrate<4, false>(v, f, cull, blocks);
+	} else {
+		if (v->bins > 0) launch_integrate<1, true>(v, f, cull, blocks);
+		else launch_integrate<1, false>(v, f, cull, blocks);
+	}
+	LAUNCH_CHECK(v);
+	CU(cudaEventRecord(v->ev_k1[slot], v->stream));
+	v->n_integrate++;
+	v->n_obs++;  // tsdf.cu:220 (counted here so the raw / device entry points keep n_obs consistent)
+	if (v->desc.flags & SFM_FLAG_SYNC_EVERY_CALL) CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int ensure_ray_buffers(sfm_volume *v, size_t px, bool want_probs) {
+	if (px > v->ray_px) {
+		cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr); cudaFree(v->d_label); cudaFree(v->d_keys);
+		v->d_t = nullptr; v->d_flags = nullptr; v->d_bgr = nullptr; v->d_label = nullptr; v->d_keys = nullptr;
+		v->ray_px = 0;
+		CU(cudaMalloc(&v->d_t, px * 4));
+		CU(cudaMalloc(&v->d_flags, px));
+		CU(cudaMalloc(&v->d_bgr, px * 3));
+		CU(cudaMalloc(&v->d_label, px));
+		CU(cudaMalloc(&v->d_keys, px * 8));
+		v->ray_px = px;
+	}
+	if (want_probs && px > v->probs_px) {
+		cudaFree(v->d_probs); cudaFree(v->d_box);
+		v->d_probs = nullptr; v->d_box = nullptr;
+		v->probs_px = 0;
+		CU(cudaMalloc(&v->d_probs, px * (size_t)v->bins * 4));
+		CU(cudaMalloc(&v->d_box, px * (size_t)v->bins));
+		v->probs_px = px;
+	}
+	return SFM_OK;
+}
+
+RayVol make_ray_vol(const sfm_volume *v) {
+	RayVol V;
+	V.sdf = v->planes.sdf;
+	V.hist = v->planes.hist;
+	V.bins = v->bins;
+	V.g = v->g;
+	return V;
+}
+
+// Rt = R(extrinsic2init)^T, o = -Rt * t   (tsdf.cu:432-435; OpenCV float gemm there)
+RayCam make_backproj_cam(const sfm_volume *v, const float *E16) {
+	RayCam c{};
+	for (int r = 0; r < 3; r++) for (int k = 0; k < 4; k++) c.M[r * 4 + k] = v->Kinv[r * 4 + k];
+	for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) c.Rt[r * 3 + k] = E16[k * 4 + r];
+	for (int r = 0; r < 3; r++) {
+		double s = 0;
+		for (int k = 0; k < 3; k++) s += (double)(-c.Rt[r * 3 + k]) * (double)E16[k * 4 + 3];
+		c.o[r] = (float)s;
+	}
+	c.show = 0;
+	c.W = v->W;
+	c.H = v->H;
+	return c;
+}
+
+RayCam make_show_cam(const float *s2w16, const float *c3, int w, int h) {
+	RayCam c{};
+	memcpy(c.M, s2w16, 12 * sizeof(float));
+	memcpy(c.o, c3, 3 * sizeof(float));
+	c.show = 1;
+	c.W = w;
+	c.H = h;
+	return c;
+}
+
+int ray_blocks(int w, int h) {
+	const long long tiles = (long long)((w + 7) / 8) * ((h + 3) / 4);
+	return (int)((tiles + 3) / 4);  // 4 warps (128 threads) per block
+}
+
+int require_full_volume(const sfm_volume *v, const char *what) {
+	if (v->g.z0 != 0 || v->g.nz != v->g.Dz)
+		return fail(SFM_ERR_INVALID, std::string(what) + ": this handle stores a z-slab; sharded ray-marching goes through sfm_raycast_keys_dev + a min-composite");
+	return SFM_OK;
+}
+
+struct FoldLayout {
+	size_t oPos, oTm, oT, oBm, oB, oCm, oNoHit, oFirst, total;
+};
+FoldLayout fold_layout(int L) {
+	FoldLayout f;
+	size_t o = 0;
+	f.oPos = o; o += (size_t)L * L * 8;
+	f.oTm = o; o += (size_t)L * L * 8;
+	f.oT = o; o += (size_t)L * 8;
+	f.oBm = o; o += (size_t)L * L * 4;
+	f.oB = o; o += (size_t)L * 4;
+	f.oCm = o; o += (size_t)L * 4;
+	f.oNoHit = o; o += (size_t)L * 4;
+	f.oFirst = o; o += (size_t)L * 4;
+	f.total = o;
+	return f;
+}
+
+// launch the fused back-project + fold on the device mask; tables end up in v->h_fold (pinned)
+int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
+	const int L = v->bins;
+	const FoldLayout fl = fold_layout(L);
+	CU(cudaMemsetAsync(v->d_fold, 0, fl.oFirst, v->stream));
+	CU(cudaMemsetAsync(v->d_fold + fl.oFirst, 0xff, (size_t)L * 4, v->stream));
+	FoldTables tb;
+	tb.Pos = (long long *)(v->d_fold + fl.oPos);
+	tb.Tm = (long long *)(v->d_fold + fl.oTm);
+	tb.T = (long long *)(v->d_fold + fl.oT);
+	tb.Bm = (unsigned *)(v->d_fold + fl.oBm);
+	tb.B = (unsigned *)(v->d_fold + fl.oB);
+	tb.Cm = (unsigned *)(v->d_fold + fl.oCm);
+	tb.NoHit = (unsigned *)(v->d_fold + fl.oNoHit);
+	tb.FirstPix = (unsigned *)(v->d_fold + fl.oFirst);
+	const RayVol V = make_ray_vol(v);
+	const RayCam cam = make_backproj_cam(v, E16);
+	const int blocks = ray_blocks(v->W, v->H);
+	const float n_obs = (float)v->n_obs, prior = v->desc.prior_err_rate, pres = v->desc.presence_thresh;
+	const int nb = (L + 31) / 32;
+	switch (nb) {
+	case 1: backproject_fold_kernel<1><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	case 2: backproject_fold_kernel<2><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	case 3: backproject_fold_kernel<3><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	case 4: backproject_fold_kernel<4><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	default: backproject_fold_kernel<8><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	}
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(v->h_fold, v->d_fold, fl.total, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+// combine the folded partial tables into the reference's A / C (see k_raymarch.cuh)
+void combine_tables(const sfm_volume *v, int max_obj_now, double *A, uint32_t *C) {
+	const int L = v->bins;
+	const FoldLayout fl = fold_layout(L);
+	const long long *Pos = (const long long *)(v->h_fold + fl.oPos);
+	const long long *Tm = (const long long *)(v->h_fold + fl.oTm);
+	const long long *T = (const long long *)(v->h_fold + fl.oT);
+	const unsigned *Bm = (const unsigned *)(v->h_fold + fl.oBm);
+	const unsigned *B = (const unsigned *)(v->h_fold + fl.oB);
+	const unsigned *Cm = (const unsigned *)(v->h_fold + fl.oCm);
+	const unsigned *NoHit = (const unsigned *)(v->h_fold + fl.oNoHit);
+	const long long logprior_fx = llrint((double)logf(v->desc.prior_err_rate) * 4294967296.0);
+	for (int m = 0; m < L; m++)
+		for (int n = 0; n < L; n++) {
+			long long a = 0;
+			uint32_t c = 0;
+			if (m >= 1 && n >= 1 && m < max_obj_now) {
+				a = Pos[m * L + n] + (long long)NoHit[m] * logprior_fx + T[n] - Tm[m * L + n];
+				c = Cm[m] + B[n] - Bm[m * L + n];
+			}
+			A[m * L + n] = (double)a / 4294967296.0;
+			C[m * L + n] = c;
+		}
+}
+
+int max_label_host(const uint8_t *mask, size_t n) {
+	uint8_t mx = 0;
+	for (size_t i = 0; i < n; i++) mx = mask[i] > mx ? mask[i] : mx;
+	return mx;
+}
+
+// decision half of filter_overlaps (tsdf.cu:335-389) from tables; fills report->assign (a LUT)
+void decide(const sfm_volume *v, const double *A, const uint32_t *C, int max_obj_now, const unsigned *first_pix,
+	int *num_objs, sfm_merge_report *rep)
+{
+	const int L = v->bins;
+	const float thr = v->desc.accept_factor * v->desc.prior_err_rate;
+	memset(rep, 0, sizeof(*rep));
+	rep->max_obj_now = max_obj_now;
+	float margin = INFINITY;
+	std::vector<int> owner(256, 0);
+	std::vector<float> owner_p(256, 0.f);
+	for (int m = 1; m < max_obj_now && m < L; m++) {
+		int best = -1;
+		float bp = 0.f, second = 0.f;
+		for (int j = 1; j < L; j++) {
+			const float p = (C[m * L + j] == 0) ? 0.f : expf((float)A[m * L + j] / (float)C[m * L + j]);
+			if (p > bp) { second = bp; best = j; bp = p; }
+			else if (p > second) second = p;
+		}
+		rep->best_prob[m] = bp;
+		if (first_pix[m] != 0xffffffffu) {  // only labels present in the frame decide anything visible
+			margin = std::min(margin, fabsf(bp - thr));
+			if (bp > thr) margin = std::min(margin, bp - second);
+		}
+		if (bp > thr) {
+			if (owner[best] == 0) { owner[best] = m; owner_p[best] = bp; }
+			else {
+				margin = std::min(margin, fabsf(owner_p[best] - bp));
+				if (owner_p[best] < bp) { owner[best] = m; owner_p[best] = bp; }
+			}
+		}
+	}
+	for (int j = 1; j < 256; j++) if (owner[j]) rep->assign[owner[j]] = j;
+	// unassigned labels that occur get fresh ids in raster order of first appearance (tsdf.cu:378-387)
+	std::vector<std::pair<unsigned, int>> fresh;
+	for (int m = 1; m < max_obj_now && m < L; m++)
+		if (!rep->assign[m] && first_pix[m] != 0xffffffffu) fresh.push_back({first_pix[m], m});
+	std::sort(fresh.begin(), fresh.end());
+	for (auto &pr : fresh) { rep->assign[pr.second] = *num_objs; (*num_objs)++; }
+	rep->num_objs = *num_objs;
+	rep->margin = margin;
+}
+
+__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) mask[i] = lut[mask[i]];
+}
+
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char *sfm_last_error(void) { return g_err.c_str(); }
+const char *sfm_version(void) { return "sfm_b200 0.1 (sm_100a)"; }
+
+void sfm_desc_default(sfm_desc *d) {
+	memset(d, 0, sizeof(*d));
+	d->dims[0] = d->dims[1] = d->dims[2] = 256;  // tsdf.cuh:52
+	d->bins = 32;                                 // tsdf.cuh:4
+	d->width = 640;
+	d->height = 480;
+	for (int i = 0; i < 4; i++) d->K[i * 4 + i] = 1.f;
+	d->K[0] = 520.9f; d->K[5] = 521.0f; d->K[2] = 325.1f; d->K[6] = 249.7f;  // kernel.cpp:39
+	d->prior_err_rate = 0.05f;
+	d->duplicate_thresh = 0.5f;
+	d->presence_thresh = 0.3f;
+	d->accept_factor = 3.f;
+	d->depth_scale = 5000.f;
+	d->trunc_voxels = 5.f;
+	d->near_gate = 0.99f;
+}
+
+void sfm_palette(uint8_t *rgb, int n) {
+	for (int i = 0; i < n; i++) memcpy(rgb + i * 3, kPalette16 + (i % 16) * 3, 3);
+}
+
+int sfm_create(const sfm_desc *desc, sfm_volume **out) {
+	if (!desc || !out) return fail(SFM_ERR_INVALID, "null argument");
+	*out = nullptr;
+	if (desc->dims[0] <= 0 || desc->dims[1] <= 0 || desc->dims[2] <= 0 || desc->dims[0] > 65535 ||
+		desc->dims[1] > 65535 || desc->dims[2] > 65535)
+		return fail(SFM_ERR_INVALID, "dims must be in [1, 65535]");
+	if (desc->bins < 0 || desc->bins > kMaxBins) return fail(SFM_ERR_INVALID, "bins must be in [0, 255]");
+	if (desc->width <= 0 || desc->height <= 0 || desc->width > 65535 || desc->height > 65535)
+		return fail(SFM_ERR_INVALID, "bad frame size");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(SFM_ERR_NODEVICE, "no CUDA device: this library has no CPU fallback");
+	}
+	if (desc->device < 0 || desc->device >= ndev) return fail(SFM_ERR_INVALID, "bad device ordinal");
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, desc->device));
+	if (prop.major != 10)
+		return fail(SFM_ERR_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+			"; the kernels are built for sm_100a only and there is no fallback");
+	CU(cudaSetDevice(desc->device));
+
+	sfm_volume *v = new sfm_volume();
+	v->desc = *desc;
+	v->bins = desc->bins;
+	v->W = desc->width;
+	v->H = desc->height;
+	v->TW = (v->W + kTile - 1) / kTile;
+	v->TH = (v->H + kTile - 1) / kTile;
+	v->g.Dx = desc->dims[0]; v->g.Dy = desc->dims[1]; v->g.Dz = desc->dims[2];
+	v->g.z0 = desc->slab_z0;
+	v->g.nz = desc->slab_nz > 0 ? desc->slab_nz : desc->dims[2] - desc->slab_z0;
+	if (v->g.z0 < 0 || v->g.nz <= 0 || v->g.z0 + v->g.nz > v->g.Dz) { delete v; return fail(SFM_ERR_INVALID, "bad z-slab"); }
+	v->nvox = (size_t)v->g.Dx * v->g.Dy * v->g.nz;
+	memcpy(v->K, desc->K, sizeof(v->K));
+	bool kinv_given = false;
+	for (int i = 0; i < 16; i++) kinv_given |= desc->Kinv[i] != 0.f;
+	if (kinv_given) memcpy(v->Kinv, desc->Kinv, sizeof(v->Kinv));
+	else if (!mat4_inv(v->K, v->Kinv)) { delete v; return fail(SFM_ERR_INVALID, "singular intrinsic matrix"); }
+
+#define CU_OR_DESTROY(call)                                                                          \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess) {                                                                     \
+			int code_ = fail(e_ == cudaErrorMemoryAllocation ? SFM_ERR_NOMEM : SFM_ERR_CUDA,         \
+				std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+			std::string keep_ = g_err;                                                               \
+			sfm_destroy(v);                                                                          \
+			g_err = keep_;                                                                           \
+			return code_;                                                                            \
+		}                                                                                            \
+	} while (0)
+
+	CU_OR_DESTROY(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+	v->own_stream = true;
+	CU_OR_DESTROY(cudaEventCreate(&v->ev_t0));
+	CU_OR_DESTROY(cudaEventCreate(&v->ev_t1));
+	for (int i = 0; i < sfm_volume::kRing; i++) {
+		CU_OR_DESTROY(cudaEventCreate(&v->ev_k0[i]));
+		CU_OR_DESTROY(cudaEventCreate(&v->ev_k1[i]));
+	}
+	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
+	CU_OR_DESTROY(cudaMalloc(&v->planes.wt, v->nvox * 4));
+	CU_OR_DESTROY(cudaMalloc(&v->planes.color, v->nvox * 3));
+	if (v->bins > 0) CU_OR_DESTROY(cudaMalloc(&v->planes.hist, v->nvox * 4 * (size_t)v->bins));
+	v->planes.bins = v->bins;
+	const size_t npx = (size_t)v->W * v->H;
+	CU_OR_DESTROY(cudaMalloc(&v->d_depth, npx * 2));
+	CU_OR_DESTROY(cudaMalloc(&v->d_rgb, npx * 3));
+	CU_OR_DESTROY(cudaMalloc(&v->d_mask, npx));
+	CU_OR_DESTROY(cudaMemset(v->d_mask, 0, npx));
+	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, (size_t)v->TW * v->TH * 2));
+	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
+	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
+	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
+	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 4));
+	CU_OR_DESTROY(cudaMalloc(&v->d_palette, 256 * 3));
+	CU_OR_DESTROY(cudaMalloc(&v->d_lut, 256));
+	{
+		uint8_t pal[256 * 3];
+		sfm_palette(pal, 256);
+		CU_OR_DESTROY(cudaMemcpy(v->d_palette, pal, sizeof(pal), cudaMemcpyHostToDevice));
+	}
+	v->frame_bytes = npx * 6;
+	for (int i = 0; i < 2; i++) {
+		CU_OR_DESTROY(cudaMallocHost(&v->pin[i].buf, v->frame_bytes));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&v->pin[i].free_ev, cudaEventDisableTiming));
+	}
+	CU_OR_DESTROY(cudaMallocHost(&v->h_stats, 2 * kStatSlots * 8));
+	CU_OR_DESTROY(cudaMallocHost(&v->h_err, 4));
+	if (v->bins > 0) {
+		v->fold_bytes = fold_layout(v->bins).total;
+		CU_OR_DESTROY(cudaMalloc(&v->d_fold, v->fold_bytes));
+		CU_OR_DESTROY(cudaMallocHost(&v->h_fold, v->fold_bytes));
+	}
+#undef CU_OR_DESTROY
+	*out = v;
+	return SFM_OK;
+}
+
+void sfm_destroy(sfm_volume *v) {
+	if (!v) return;
+	cudaSetDevice(v->desc.device);
+	if (v->stream) cudaStreamSynchronize(v->stream);
+	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist);
+	cudaFree(v->d_depth); cudaFree(v->d_rgb); cudaFree(v->d_mask); cudaFree(v->d_tilemax); cudaFree(v->d_stats);
+	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
+	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
+	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_fold);
+	for (int i = 0; i < 2; i++) {
+		if (v->pin[i].buf) cudaFreeHost(v->pin[i].buf);
+		if (v->pin[i].free_ev) cudaEventDestroy(v->pin[i].free_ev);
+	}
+	if (v->h_stats) cudaFreeHost(v->h_stats);
+	if (v->h_err) cudaFreeHost(v->h_err);
+	if (v->h_fold) cudaFreeHost(v->h_fold);
+	if (v->ev_t0) cudaEventDestroy(v->ev_t0);
+	if (v->ev_t1) cudaEventDestroy(v->ev_t1);
+	for (int i = 0; i < sfm_volume::kRing; i++) {
+		if (v->ev_k0[i]) cudaEventDestroy(v->ev_k0[i]);
+		if (v->ev_k1[i]) cudaEventDestroy(v->ev_k1[i]);
+	}
+	if (v->own_stream && v->stream) cudaStreamDestroy(v->stream);
+	cudaGetLastError();
+	delete v;
+}
+
+int sfm_set_bounds(sfm_volume *v, const float *vol_start3, const float *vol_end3, const float *voxel3, float miu) {
+	if (!v || !vol_start3 || !vol_end3 || !voxel3) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	v->g.sx = vol_start3[0]; v->g.sy = vol_start3[1]; v->g.sz = vol_start3[2];
+	v->g.ex = vol_end3[0]; v->g.ey = vol_end3[1]; v->g.ez = vol_end3[2];
+	v->g.vx = voxel3[0]; v->g.vy = voxel3[1]; v->g.vz = voxel3[2];
+	v->g.miu = miu;
+	v->init = true;
+	for (int i = 0; i < 16; i++) v->init_extr_inv[i] = (i % 5 == 0) ? 1.f : 0.f;
+	return reset_planes(v);
+}
+
+int sfm_init_from_frame(sfm_volume *v, const uint16_t *depth, const float *extrinsic16, float mean_depth) {
+	if (!v || !depth || !extrinsic16) return fail(SFM_ERR_INVALID, "null argument");
+	// tsdf.cu:180-182: bounding rectangle of depth != 0 (the saturating cast to u8 keeps nonzero nonzero)
+	int x0 = v->W, y0 = v->H, x1 = -1, y1 = -1;
+	for (int y = 0; y < v->H; y++)
+		for (int x = 0; x < v->W; x++)
+			if (depth[(size_t)y * v->W + x]) { x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y); }
+	if (x1 < 0) return fail(SFM_ERR_INVALID, "first depth frame has no valid pixel");
+	// cv::Rect: tl = (x0,y0), br = (x0+width, y0+height) = (x1+1, y1+1)
+	const float tlp[4] = {(float)x0, (float)y0, 1.f, 1.f}, brp[4] = {(float)(x1 + 1), (float)(y1 + 1), 1.f, 1.f};
+	float tl[4], br[4];
+	for (int r = 0; r < 4; r++) {  // tsdf.cu:185-188  Kinv(4x4) * p, then * mean_depth
+		double a = 0, b = 0;
+		for (int k = 0; k < 4; k++) { a += (double)v->Kinv[r * 4 + k] * tlp[k]; b += (double)v->Kinv[r * 4 + k] * brp[k]; }
+		tl[r] = (float)a * mean_depth;
+		br[r] = (float)b * mean_depth;
+	}
+	// tsdf.cu:193: sqrt(pow(dx,2)+pow(dy,2))/2 evaluated in double, stored to float
+	const float half_side = (float)(sqrt(pow((double)(tl[0] - br[0]), 2) + pow((double)(tl[1] - br[1]), 2)) / 2);
+	float start[3], end[3], voxel[3];
+	const int dims[3] = {v->g.Dx, v->g.Dy, v->g.Dz};
+	for (int a = 0; a < 3; a++) {
+		const float center = (tl[a] + br[a]) / 2;      // tsdf.cu:194
+		start[a] = center - half_side;                 // tsdf.cu:195
+		end[a] = center + half_side;                   // tsdf.cu:196
+		voxel[a] = (end[a] - start[a]) / (float)(dims[a] - 1);  // tsdf.cu:197 (cv::divide in f32)
+	}
+	const float miu = v->desc.trunc_voxels * voxel[0];  // tsdf.cu:199
+	int rc = sfm_set_bounds(v, start, end, voxel, miu);
+	if (rc) return rc;
+	v->mean_depth = mean_depth;                         // tsdf.cu:191
+	if (!mat4_inv(extrinsic16, v->init_extr_inv)) return fail(SFM_ERR_INVALID, "singular first extrinsic");  // tsdf.cu:177
+	return SFM_OK;
+}
+
+int sfm_integrate_dev(sfm_volume *v, const void *d_depth, const void *d_color, const void *d_mask, const float *E16) {
+	if (!v || !d_depth || !d_color || !E16 || (v->bins > 0 && !d_mask)) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	return integrate_device(v, d_depth, d_color, d_mask, E16);
+}
+
+int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask, const float *E16) {
+	if (!v || !depth || !color || !E16 || (v->bins > 0 && !mask)) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	int rc = upload_frame(v, depth, color, v->bins > 0 ? mask : nullptr);
+	if (rc) return rc;
+	return integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+}
+
+int sfm_overlap_tables(sfm_volume *v, const float *E16, const uint8_t *mask, double *A, uint32_t *C) {
+	if (!v || !E16 || !mask || !A || !C) return fail(SFM_ERR_INVALID, "null argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	if (!v->init || v->n_obs == 0) return fail(SFM_ERR_INVALID, "no observation integrated yet (tsdf.cu:426)");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_overlap_tables");
+	if (rc) return rc;
+	const size_t npx = (size_t)v->W * v->H;
+	const int mx = max_label_host(mask, npx);
+	if (mx >= v->bins) return fail(SFM_ERR_INVALID, "mask carries a label >= bins");
+	rc = upload_frame(v, nullptr, nullptr, mask);
+	if (rc) return rc;
+	rc = run_fold(v, E16, v->d_mask);
+	if (rc) return rc;
+	combine_tables(v, mx + 1, A, C);
+	return SFM_OK;
+}
+
+int sfm_merge_decide(sfm_volume *v, const double *A, const uint32_t *C, uint8_t *mask_inout, sfm_merge_report *report) {
+	if (!v || !A || !C || !mask_inout) return fail(SFM_ERR_INVALID, "null argument");
+	const size_t npx = (size_t)v->W * v->H;
+	const int mx = max_label_host(mask_inout, npx);
+	if (mx >= v->bins) return fail(SFM_ERR_INVALID, "mask carries a label >= bins");
+	std::vector<unsigned> first(256, 0xffffffffu);
+	for (size_t i = 0; i < npx; i++) if (first[mask_inout[i]] == 0xffffffffu) first[mask_inout[i]] = (unsigned)i;
+	sfm_merge_report rep;
+	decide(v, A, C, mx + 1, first.data(), &v->num_objs, &rep);
+	for (size_t i = 0; i < npx; i++) mask_inout[i] = (uint8_t)rep.assign[mask_inout[i]];
+	v->last_merge = rep;
+	if (report) *report = rep;
+	return SFM_OK;
+}
+
+int sfm_last_merge(sfm_volume *v, sfm_merge_report *report) {
+	if (!v || !report) return fail(SFM_ERR_INVALID, "null argument");
+	*report = v->last_merge;
+	return SFM_OK;
+}
+
+int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout, const float *E16) {
+	if (!v || !depth || !color || !E16 || (v->bins > 0 && !mask_inout)) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	const size_t npx = (size_t)v->W * v->H;
+	int rc;
+	if (v->bins > 0) {
+		const int mx = max_label_host(mask_inout, npx);
+		if (mx >= v->bins) return fail(SFM_ERR_INVALID, "mask carries a label >= bins");
+		rc = upload_frame(v, depth, color, mask_inout);
+		if (rc) return rc;
+		if (v->n_obs > 0) {
+			// tsdf.cu:426-461: back-project, fold, decide, relabel
+			rc = require_full_volume(v, "sfm_fuse_frame (merge)");
+			if (rc) return rc;
+			rc = run_fold(v, E16, v->d_mask);
+			if (rc) return rc;
+			const int L = v->bins;
+			std::vector<double> A((size_t)L * L);
+			std::vector<uint32_t> C((size_t)L * L);
+			combine_tables(v, mx + 1, A.data(), C.data());
+			const unsigned *first = (const unsigned *)(v->h_fold + fold_layout(L).oFirst);
+			sfm_merge_report rep;
+			decide(v, A.data(), C.data(), mx + 1, first, &v->num_objs, &rep);
+			v->last_merge = rep;
+			int newmax = 0;
+			uint8_t lut[256];
+			for (int m = 0; m < 256; m++) { lut[m] = (uint8_t)rep.assign[m]; if (m <= mx) newmax = std::max(newmax, rep.assign[m]); }
+			if (newmax >= L)
+				return fail(SFM_ERR_INVALID, "merge produced a global instance id >= bins (num_objs outgrew the histogram; the reference overflows here, tsdf.cu:61,383)");
+			// relabel on the device (LUT) and on the caller's host mask (tsdf.cu:372-389 does it in place)
+			CU(cudaMemcpyAsync(v->d_lut, lut, 256, cudaMemcpyHostToDevice, v->stream));
+			relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(v->d_mask, (int)npx, v->d_lut);
+			LAUNCH_CHECK(v);
+			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+			if (rc) return rc;
+			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // overlaps the kernel
+			CU(cudaStreamSynchronize(v->stream));  // lut (stack) must outlive the async copy
+		} else {
+			v->num_objs = mx + 1;  // tsdf.cu:464-467
+			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+			if (rc) return rc;
+		}
+	} else {
+		rc = upload_frame(v, depth, color, nullptr);
+		if (rc) return rc;
+		rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+		if (rc) return rc;
+	}
+	return SFM_OK;
+}
+
+int sfm_parse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
+	const float *extrinsic16, float mean_depth)
+{
+	if (!v || !depth || !extrinsic16) return fail(SFM_ERR_INVALID, "null argument");
+	if (!v->init) return sfm_init_from_frame(v, depth, extrinsic16, mean_depth);  // tsdf.cu:173-214
+	float e2i[16];
+	mat4_mul(extrinsic16, v->init_extr_inv, e2i);  // tsdf.cu:217
+	return sfm_fuse_frame(v, depth, color, mask_inout, e2i);
+}
+
+int sfm_backproject(sfm_volume *v, const float *E16, float *probs, uint8_t *box_mask, float *t_out, uint8_t *flags_out) {
+	if (!v || !E16 || !probs || !box_mask) return fail(SFM_ERR_INVALID, "null argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_backproject");
+	if (rc) return rc;
+	const size_t npx = (size_t)v->W * v->H;
+	rc = ensure_ray_buffers(v, npx, true);
+	if (rc) return rc;
+	CU(cudaMemsetAsync(v->d_probs, 0, npx * v->bins * 4, v->stream));  // tsdf.cu:428-429
+	CU(cudaMemsetAsync(v->d_box, 0, npx * v->bins, v->stream));
+	backproject_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16),
+		v->desc.presence_thresh, v->d_probs, v->d_box, v->d_t, v->d_flags);
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(probs, v->d_probs, npx * v->bins * 4, cudaMemcpyDeviceToHost, v->stream));  // tsdf.cu:457-458
+	CU(cudaMemcpyAsync(box_mask, v->d_box, npx * v->bins, cudaMemcpyDeviceToHost, v->stream));
+	if (t_out) CU(cudaMemcpyAsync(t_out, v->d_t, npx * 4, cudaMemcpyDeviceToHost, v->stream));
+	if (flags_out) CU(cudaMemcpyAsync(flags_out, v->d_flags, npx, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, void *d_keys) {
+	if (!v || !s2w16 || !c3 || !d_keys || w <= 0 || h <= 0) return fail(SFM_ERR_INVALID, "bad argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_raycast_keys_dev");
+	if (rc) return rc;
+	raycast_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_palette,
+		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, uint8_t *bgr, float *t_opt, uint8_t *label_opt) {
+	if (!v || !s2w16 || !c3 || !bgr || w <= 0 || h <= 0 || w > 65535 || h > 65535) return fail(SFM_ERR_INVALID, "bad argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_raycast");
+	if (rc) return rc;
+	const size_t npx = (size_t)w * h;
+	rc = ensure_ray_buffers(v, npx, false);
+	if (rc) return rc;
+	raycast_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_palette,
+		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags);
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));  // viewer.cu:167
+	if (t_opt) CU(cudaMemcpyAsync(t_opt, v->d_t, npx * 4, cudaMemcpyDeviceToHost, v->stream));
+	if (label_opt) CU(cudaMemcpyAsync(label_opt, v->d_label, npx, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_ray_flags(sfm_volume *v, uint8_t *flags, size_t n) {
+	if (!v || !flags) return fail(SFM_ERR_INVALID, "null argument");
+	if (n > v->ray_px) return fail(SFM_ERR_INVALID, "no ray-march of that size has run");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemcpyAsync(flags, v->d_flags, n, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_keys_to_bgr(sfm_volume *v, const void *d_keys, int w, int h, uint8_t *bgr) {
+	if (!v || !d_keys || !bgr || w <= 0 || h <= 0) return fail(SFM_ERR_INVALID, "bad argument");
+	CU(cudaSetDevice(v->desc.device));
+	const size_t npx = (size_t)w * h;
+	int rc = ensure_ray_buffers(v, npx, false);
+	if (rc) return rc;
+	keys_to_bgr_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>((const unsigned long long *)d_keys, v->d_palette,
+		(int)npx, v->d_bgr);
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+void sfm_orbit_camera(const float *Kinv16, float angle, float dist, float *s2w16, float *c3) {
+	// viewer.cu:140-146
+	const float rot[16] = {cosf(angle), 0, -sinf(angle), dist * sinf(angle), 0, 1, 0, 0,
+		sinf(angle), 0, cosf(angle), dist - dist * cosf(angle), 0, 0, 0, 1};
+	mat4_mul(rot, Kinv16, s2w16);
+	c3[0] = (dist + 0.5f) * sinf(angle);
+	c3[1] = 0.f;
+	c3[2] = (dist + 0.5f) - (dist + 0.5f) * cosf(angle);
+}
+
+int sfm_show(sfm_volume *v, float angle, float dist, int w, int h, uint8_t *bgr) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	float s2w[16], c[3];
+	sfm_orbit_camera(v->Kinv, angle, dist, s2w, c);
+	return sfm_raycast(v, s2w, c, w, h, bgr, nullptr, nullptr);
+}
+
+size_t sfm_plane_bytes(sfm_volume *v, int plane) { return v ? v->nvox * plane_elem_bytes(v, plane) : 0; }
+void *sfm_plane_device_ptr(sfm_volume *v, int plane) { return v ? plane_ptr(v, plane) : nullptr; }
+
+int sfm_download(sfm_volume *v, int plane, void *dst, size_t bytes) {
+	if (!v || !dst) return fail(SFM_ERR_INVALID, "null argument");
+	const size_t need = sfm_plane_bytes(v, plane);
+	if (!need || bytes != need) return fail(SFM_ERR_INVALID, "plane / size mismatch");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemcpyAsync(dst, plane_ptr(v, plane), need, cudaMemcpyDeviceToHost, v->stream));
+	return check_device_error(v);
+}
+
+int sfm_upload(sfm_volume *v, int plane, const void *src, size_t bytes) {
+	if (!v || !src) return fail(SFM_ERR_INVALID, "null argument");
+	const size_t need = sfm_plane_bytes(v, plane);
+	if (!need || bytes != need) return fail(SFM_ERR_INVALID, "plane / size mismatch");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemcpyAsync(plane_ptr(v, plane), src, need, cudaMemcpyHostToDevice, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_get_info(sfm_volume *v, sfm_info *info) {
+	if (!v || !info) return fail(SFM_ERR_INVALID, "null argument");
+	memset(info, 0, sizeof(*info));
+	info->dims[0] = v->g.Dx; info->dims[1] = v->g.Dy; info->dims[2] = v->g.Dz;
+	info->bins = v->bins;
+	info->width = v->W; info->height = v->H;
+	info->slab_z0 = v->g.z0; info->slab_nz = v->g.nz;
+	info->vol_start[0] = v->g.sx; info->vol_start[1] = v->g.sy; info->vol_start[2] = v->g.sz;
+	info->vol_end[0] = v->g.ex; info->vol_end[1] = v->g.ey; info->vol_end[2] = v->g.ez;
+	info->voxel[0] = v->g.vx; info->voxel[1] = v->g.vy; info->voxel[2] = v->g.vz;
+	info->miu = v->g.miu;
+	info->mean_depth = v->mean_depth;
+	info->n_obs = v->n_obs;
+	info->num_objs = v->num_objs;
+	info->initialised = v->init ? 1 : 0;
+	return SFM_OK;
+}
+
+int sfm_synchronize(sfm_volume *v) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	return check_device_error(v);
+}
+
+int sfm_set_stream(sfm_volume *v, void *cuda_stream) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaStreamSynchronize(v->stream));
+	if (v->own_stream) cudaStreamDestroy(v->stream);
+	v->stream = (cudaStream_t)cuda_stream;
+	v->own_stream = false;
+	return SFM_OK;
+}
+
+int sfm_timer_start(sfm_volume *v) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaEventRecord(v->ev_t0, v->stream));
+	return SFM_OK;
+}
+
+int sfm_timer_stop(sfm_volume *v, float *ms) {
+	if (!v || !ms) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaEventRecord(v->ev_t1, v->stream));
+	CU(cudaEventSynchronize(v->ev_t1));
+	CU(cudaEventElapsedTime(ms, v->ev_t0, v->ev_t1));
+	return SFM_OK;
+}
+
+uint64_t sfm_launch_count(sfm_volume *v) { return v ? v->launches : 0; }
+
+int sfm_integrate_times(sfm_volume *v, float *ms, int n) {
+	if (!v || !ms || n < 0) return fail(SFM_ERR_INVALID, "bad argument");
+	if ((uint64_t)n > v->n_integrate || n > sfm_volume::kRing) return fail(SFM_ERR_INVALID, "fewer integrate calls recorded than requested");
+	for (int i = 0; i < n; i++) {
+		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
+		CU(cudaEventSynchronize(v->ev_k1[slot]));
+		CU(cudaEventElapsedTime(ms + i, v->ev_k0[slot], v->ev_k1[slot]));
+	}
+	return SFM_OK;
+}
+
+int sfm_last_integrate_ms(sfm_volume *v, float *ms) { return sfm_integrate_times(v, ms, 1); }
+
+/* U = voxels whose weight was incremented, S = voxels whose colour/histogram was updated, summed
+ * over the integrate calls since the previous sfm_frame_stats call. */
+int sfm_frame_stats(sfm_volume *v, uint64_t *U, uint64_t *S) {
+	if (!v || !U || !S) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemcpyAsync(v->h_stats, v->d_stats, 2 * kStatSlots * 8, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	uint64_t u = 0, s = 0;
+	for (int i = 0; i < kStatSlots; i++) { u += v->h_stats[i]; s += v->h_stats[kStatSlots + i]; }
+	*U = u - v->stat_U_seen;
+	*S = s - v->stat_S_seen;
+	v->stat_U_seen = u;
+	v->stat_S_seen = s;
+	return SFM_OK;
+}
+
+float sfm_mean_depth(const uint16_t *depth, int n) {  // utils.cu:77-91
+	double sum = 0;
+	int total = 0;
+	for (int i = 0; i < n; i++) {
+		if (depth[i] == 0) continue;
+		sum += depth[i] / 5000.;
+		total++;
+	}
+	return static_cast<float>(sum / total);
+}
+
+void sfm_parse_extrinsic(const double *p, float *extrinsic16) {  // utils.cu:8-24
+	const double ax = p[3], ay = p[4], az = p[5];
+	const double n = sqrt(ax * ax + ay * ay + az * az);
+	const double theta = 2 * atan2(n, p[6]);
+	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	if (n > 0 && theta != 0) {  // Rodrigues(theta * axis)
+		const double rx = ax / n, ry = ay / n, rz = az / n, c = cos(theta), s = sin(theta), c1 = 1 - c;
+		R[0] = c + c1 * rx * rx;      R[1] = c1 * rx * ry - s * rz; R[2] = c1 * rx * rz + s * ry;
+		R[3] = c1 * ry * rx + s * rz; R[4] = c + c1 * ry * ry;      R[5] = c1 * ry * rz - s * rx;
+		R[6] = c1 * rz * rx - s * ry; R[7] = c1 * rz * ry + s * rx; R[8] = c + c1 * rz * rz;
+	}
+	float m[16] = {(float)R[0], (float)R[1], (float)R[2], (float)p[0], (float)R[3], (float)R[4], (float)R[5], (float)p[1],
+		(float)R[6], (float)R[7], (float)R[8], (float)p[2], 0, 0, 0, 1};
+	if (!mat4_inv(m, extrinsic16)) memcpy(extrinsic16, m, sizeof(m));
+}
+
+}  // extern "C"

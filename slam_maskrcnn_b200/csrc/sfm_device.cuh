@@ -1,0 +1,78 @@
+// sfm_device.cuh -- shared device-side types and exact-arithmetic helpers (sm_100a).
+//
+// Bit-exactness contract: every floating-point operation that decides an
+// integer result is written with explicit round-to-nearest intrinsics (__fmaf_rn, __fmul_rn,
+// __fadd_rn, __fdiv_rn) in the order the reference's compiled code evaluates them, so that this
+// translation unit's own compiler flags can never re-contract or re-associate them.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sfm {
+
+constexpr int kTile = 8;           // depth tile edge (pixels) of the per-frame max-depth grid
+constexpr int kStatSlots = 256;    // spread slots for the per-frame U/S counters
+constexpr int kMaxBins = 255;
+
+struct VolGeom {
+	int Dx, Dy, Dz;  // global volume dimensions (vol_dim_, tsdf.cuh:52)
+	int z0, nz;      // z-slab stored by this handle: global planes [z0, z0+nz)
+	float sx, sy, sz;  // vol_start_
+	float ex, ey, ez;  // vol_end_
+	float vx, vy, vz;  // vol_res_
+	float miu;
+};
+
+struct Planes {
+	float *sdf;
+	int32_t *wt;
+	uint8_t *color;
+	uint32_t *hist;
+	int bins;
+};
+
+struct FrameView {
+	const uint16_t *depth;
+	const uint8_t *rgb;
+	const uint8_t *mask;
+	const uint16_t *tilemax;  // [TH][TW] max depth per kTile x kTile tile
+	int W, H, TW, TH;
+	float E[12];  // rows 0..2 of extrinsic2init (row-major 3x4)
+	float K[9];   // rows 0..2, cols 0..2 of the intrinsic matrix
+	float depth_scale, near_gate;
+	// conservative-cull constants, computed on the host per frame (see k_integrate.cuh)
+	float cull_lin;     // max_r sum_c |E[r][c]|, c<3: amplification of voxel coordinates
+	float cull_t;       // max_r |E[r][3]|
+	float cull_k2;      // |K20|+|K21|+|K22|
+	float cull_slack0;  // constant pixel slack
+};
+
+// dot(float4 row,(p,1)) as the reference compiles it (helper_math.h:1249-1252; tsdf.cu:31-33):
+//   r3 + fma(pz, r2, fma(px, r0, py*r1)).   `h` is the z-invariant part fma(px,r0,py*r1).
+__device__ __forceinline__ float affine_hoist(float px, float py, float r0, float r1) {
+	return __fmaf_rn(px, r0, __fmul_rn(py, r1));
+}
+__device__ __forceinline__ float affine_finish(float h, float pz, float r2, float r3) {
+	return __fadd_rn(r3, __fmaf_rn(pz, r2, h));
+}
+// dot(float3,float3) as compiled (helper_math.h:1245-1248): fma(bz,az, fma(bx,ax, by*ay))
+__device__ __forceinline__ float dot3_ref(float a0, float a1, float a2, float bx, float by, float bz) {
+	return __fmaf_rn(bz, a2, __fmaf_rn(bx, a0, __fmul_rn(by, a1)));
+}
+// mix (utils.cu:93-96) as compiled: fma(a, 1-t, t*b)
+__device__ __forceinline__ float mix_ref(float a, float b, float t) {
+	return __fmaf_rn(a, __fadd_rn(1.f, -t), __fmul_rn(t, b));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+}  // namespace sfm

@@ -1,0 +1,137 @@
+"""K1 parity: the CUDA integrate path (through the C-ABI) against
+  (1) the reference's own tsdf_kernel compiled verbatim (oracle/_ref) on the same GPU, and
+  (2) the CPU C restatement (oracle/liboracle.so),
+bit-exact on every plane: SDF (compared as raw bits), weight, colour, histogram."""
+import numpy as np
+import pytest
+
+from tests.common import Scenario, bits
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ours(sc, flags=0, labels=True, mask_key="gt"):
+    v = sc.make_volume(flags=flags, bins=sc.bins if labels else 0)
+    stats = []
+    for fr in sc.frames:
+        v.integrate_raw(fr["depth"], fr["color"], fr[mask_key] if labels else None, fr["extrinsic"])
+        stats.append(v.frame_stats())
+    out = {k: v.download(k) for k in (("sdf", "weight", "color", "hist") if labels else ("sdf", "weight", "color"))}
+    v.close()
+    return out, stats
+
+
+def run_cpu_oracle(sc, labels=True, mask_key="gt"):
+    cv = sc.make_cpu_volume(bins=sc.bins if labels else 0)
+    stats = []
+    for fr in sc.frames:
+        stats.append(cv.integrate(sc.K, fr["depth"], fr["color"], fr[mask_key], fr["extrinsic"], sc.W, sc.H))
+    return cv.planes(), stats
+
+
+def run_reference_kernel(sc, mask_key="gt"):
+    import torch
+    from oracle import binding as ob
+    n = int(np.prod(sc.dims))
+    dev = "cuda"
+    sdf = torch.full((n,), float(sc.miu), dtype=torch.float32, device=dev)
+    wt = torch.zeros(n, dtype=torch.int32, device=dev)
+    col = torch.zeros(n * 3, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(n * sc.bins, dtype=torch.int32, device=dev)
+    for fr in sc.frames:
+        d = torch.from_numpy(fr["depth"].view(np.int16)).to(dev)
+        c = torch.from_numpy(fr["color"]).to(dev)
+        m = torch.from_numpy(fr[mask_key]).to(dev)
+        torch.cuda.synchronize()
+        ob.ref_integrate(sc.bins, sdf.data_ptr(), col.data_ptr(), cnt.data_ptr(), wt.data_ptr(), sc.dims, sc.start,
+                         sc.voxel, float(sc.miu), sc.K, d.data_ptr(), c.data_ptr(), m.data_ptr(), fr["extrinsic"], sc.W, sc.H)
+    sh = sc.dims
+    return {"sdf": sdf.cpu().numpy().reshape(sh), "weight": wt.cpu().numpy().reshape(sh),
+            "color": col.cpu().numpy().reshape(sh + (3,)), "hist": cnt.cpu().numpy().view(np.uint32).reshape(sh + (sc.bins,))}
+
+
+def assert_planes_equal(a, b, what):
+    for k in a:
+        if k == "sdf":
+            same = bits(a[k]) == bits(b[k])
+        else:
+            same = a[k] == b[k]
+        assert same.all(), f"{what}: plane {k} differs at {int((~same).sum())} of {same.size} entries"
+
+
+@pytest.mark.parametrize("dims,bins", [((64, 64, 64), 16), ((48, 40, 36), 32), ((33, 31, 30), 16), ((40, 40, 29), 32)])
+def test_integrate_matches_reference_kernel(dims, bins):
+    from oracle import binding as ob
+    if not ob.ref_available(bins):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=dims, bins=bins, frames=5)
+    ours, stats = run_ours(sc)
+    ref = run_reference_kernel(sc)
+    assert_planes_equal(ours, ref, "vs reference tsdf_kernel")
+    assert ours["weight"].sum() == sum(u for u, _ in stats)
+    assert ours["hist"].sum() == sum(s for _, s in stats)
+    assert ours["weight"].sum() > 0 and ours["hist"].sum() > 0
+
+
+@pytest.mark.parametrize("dims", [(64, 64, 64), (33, 31, 30)])
+def test_integrate_matches_cpu_oracle(dims):
+    sc = Scenario(dims=dims, bins=16, frames=4)
+    ours, stats = run_ours(sc)
+    orc, ostats = run_cpu_oracle(sc)
+    assert_planes_equal(ours, orc, "vs CPU oracle")
+    assert stats == ostats
+
+
+def test_cull_is_exact():
+    """Brick culling must not change a single bit (it only skips voxels the reference rejects)."""
+    from slam_maskrcnn_b200 import FLAG_NO_CULL
+    sc = Scenario(dims=(96, 96, 96), bins=16, frames=6, yaw_step_deg=4.0)
+    a, sa = run_ours(sc, flags=0)
+    b, sb = run_ours(sc, flags=FLAG_NO_CULL)
+    assert_planes_equal(a, b, "cull vs no-cull")
+    assert sa == sb
+
+
+def test_labels_off_mode():
+    """bins == 0: a1 minus the histogram increment; SDF / weight / colour unchanged."""
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=3)
+    on, _ = run_ours(sc, labels=True)
+    off, _ = run_ours(sc, labels=False)
+    for k in ("sdf", "weight", "color"):
+        assert (bits(on[k]) == bits(off[k])).all() if k == "sdf" else (on[k] == off[k]).all()
+
+
+def test_permuted_noisy_labels_match_reference():
+    from oracle import binding as ob
+    if not ob.ref_available(16):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=4, permute=True)
+    ours, _ = run_ours(sc, mask_key="mask")
+    ref = run_reference_kernel(sc, mask_key="mask")
+    assert_planes_equal(ours, ref, "noisy labels vs reference tsdf_kernel")
+
+
+def test_label_out_of_range_is_rejected():
+    from slam_maskrcnn_b200 import SfmError
+    sc = Scenario(dims=(32, 32, 32), bins=16, frames=1)
+    v = sc.make_volume()
+    fr = sc.frames[0]
+    bad = fr["gt"].copy()
+    bad[10, 10] = 16
+    v.integrate_raw(fr["depth"], fr["color"], bad, fr["extrinsic"])
+    with pytest.raises(SfmError):
+        v.synchronize()
+    v.close()
+
+
+def test_full_size_frame_256_matches_reference_kernel():
+    """BASELINE config 1 shape: 640x480 frames, 256^3, 16 bins (3 frames to keep it quick)."""
+    from oracle import binding as ob
+    if not ob.ref_available(16):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=(256, 256, 256), bins=16, width=640, height=480, n_instances=15, frames=3, yaw_step_deg=2.0)
+    ours, stats = run_ours(sc)
+    ref = run_reference_kernel(sc)
+    assert_planes_equal(ours, ref, "256^3 vs reference tsdf_kernel")
+    u = sum(u for u, _ in stats)
+    assert 0.03 < u / (3 * 256 ** 3) < 0.4

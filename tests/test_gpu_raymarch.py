@@ -1,0 +1,230 @@
+"""K2 / K3 parity: back-projection, fused overlap fold, merge decisions and ray-cast (through the
+C-ABI) against the reference's own back_proj_kernel / show_tsdf_kernel / filter_overlaps compiled
+verbatim (oracle/_ref), on the same GPU and the same fused volume.
+
+The reference reads out of bounds when a trilinear tap falls on a volume face (SURVEY appendix
+B.2); our taps are clamped and such rays are flagged.  The reference's buffers are therefore
+embedded in guard-padded allocations, and bit-exactness is asserted on the unflagged rays."""
+import numpy as np
+import pytest
+
+from tests.common import Scenario, backproj_camera, bits
+
+pytestmark = pytest.mark.gpu
+
+
+class FusedPair:
+    """Our volume after a few integrated frames + a guard-padded device copy for the reference kernels."""
+
+    def __init__(self, sc, nframes=None, mask_key="gt"):
+        import torch
+        self.sc = sc
+        self.vol = sc.make_volume()
+        for fr in sc.frames[:nframes]:
+            self.vol.integrate_raw(fr["depth"], fr["color"], fr[mask_key], fr["extrinsic"])
+        self.n = int(np.prod(sc.dims))
+        self.pad = 2 * sc.dims[1] * sc.dims[2] + 64
+        self.sync_reference_copy()
+
+    def sync_reference_copy(self):
+        import torch
+        sc, n, pad = self.sc, self.n, self.pad
+        sdf = self.vol.download("sdf").reshape(-1)
+        hist = self.vol.download("hist").reshape(-1)
+        col = self.vol.download("color").reshape(-1)
+        self.sdf_buf = torch.full((n + 2 * pad,), float(sc.miu), dtype=torch.float32, device="cuda")
+        self.sdf_buf[pad:pad + n] = torch.from_numpy(sdf).cuda()
+        self.cnt_buf = torch.zeros((n + 2 * pad) * sc.bins, dtype=torch.int32, device="cuda")
+        self.cnt_buf[pad * sc.bins:(pad + n) * sc.bins] = torch.from_numpy(hist.view(np.int32)).cuda()
+        self.col_buf = torch.zeros((n + 2 * pad) * 3, dtype=torch.uint8, device="cuda")
+        self.col_buf[pad * 3:(pad + n) * 3] = torch.from_numpy(col).cuda()
+        torch.cuda.synchronize()
+
+    @property
+    def sdf_ptr(self):
+        return self.sdf_buf.data_ptr() + self.pad * 4
+
+    @property
+    def cnt_ptr(self):
+        return self.cnt_buf.data_ptr() + self.pad * self.sc.bins * 4
+
+    @property
+    def col_ptr(self):
+        return self.col_buf.data_ptr() + self.pad * 3
+
+
+def reference_backproject(fp, E):
+    import torch
+    from oracle import binding as ob
+    sc = fp.sc
+    Rt, o = backproj_camera(E)
+    probs = torch.zeros(sc.H * sc.W * sc.bins, dtype=torch.float32, device="cuda")
+    box = torch.zeros(sc.H * sc.W * sc.bins, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ob.ref_back_proj(sc.bins, sc.Kinv, Rt, o, sc.start, sc.end, sc.voxel, sc.dims, fp.sdf_ptr, fp.cnt_ptr, sc.W, sc.H,
+                     probs.data_ptr(), box.data_ptr())
+    return probs.cpu().numpy().reshape(sc.H, sc.W, sc.bins), box.cpu().numpy().reshape(sc.H, sc.W, sc.bins)
+
+
+@pytest.mark.parametrize("dims,bins", [((64, 64, 64), 16), ((80, 72, 64), 32)])
+def test_backproject_matches_reference_kernel(dims, bins):
+    from oracle import binding as ob
+    if not ob.ref_available(bins):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=dims, bins=bins, frames=6, yaw_step_deg=2.0)
+    fp = FusedPair(sc, nframes=5)
+    E = sc.frames[5]["extrinsic"]
+    probs, box, t, flags = fp.vol.backproject(E)
+    rprobs, rbox = reference_backproject(fp, E)
+    ok = flags == 0
+    assert ok.mean() > 0.9, f"too many boundary-clamped rays: {1 - ok.mean():.3f}"
+    hit = t > 0
+    assert hit.mean() > 0.3, "scene should produce surface hits"
+    assert (bits(probs)[ok] == bits(rprobs)[ok]).all(), "probs differ on in-bounds rays"
+    assert (box[ok] == rbox[ok]).all()
+    # hit set must agree too: a reference hit has some non-zero probs row or not -- compare via sums
+    assert ((probs.sum(-1) > 0) == (rprobs.sum(-1) > 0))[ok].all()
+    fp.vol.close()
+
+
+def test_fused_fold_tables_match_materialised_probs():
+    """sfm_overlap_tables (fused, fixed-point) vs tables accumulated in float64 from the materialised probs."""
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=6, yaw_step_deg=2.0, permute=True)
+    fp = FusedPair(sc, nframes=5)
+    fr = sc.frames[5]
+    E, mask = fr["extrinsic"], fr["mask"]
+    probs, box, t, flags = fp.vol.backproject(E)
+    n_obs = fp.vol.info().n_obs
+    assert n_obs == 5
+    A, Cn = fp.vol.overlap_tables(E, mask)
+    L = sc.bins
+    prior = np.float32(0.05)
+    max_obj_now = int(mask.max()) + 1
+    P = probs.reshape(-1, L)
+    M = mask.reshape(-1)
+    pos = np.log(np.maximum(P / np.float32(n_obs), prior).astype(np.float32).astype(np.float64))
+    neg = np.log(np.maximum(np.float32(1) - P / np.float32(n_obs), prior).astype(np.float32).astype(np.float64))
+    boxm = P > np.float32(0.3)
+    A64 = np.zeros((L, L))
+    C64 = np.zeros((L, L), np.int64)
+    for m in range(1, max_obj_now):
+        sel = M == m
+        A64[m, 1:] += pos[sel][:, 1:].sum(0)
+        C64[m, 1:] += sel.sum()
+        other = ~sel
+        A64[m, 1:] += (neg[other][:, 1:] * boxm[other][:, 1:]).sum(0)
+        C64[m, 1:] += boxm[other][:, 1:].sum(0)
+    assert (Cn.astype(np.int64) == C64).all(), "overlap counts must be exact"
+    np.testing.assert_allclose(A, A64, rtol=2e-6, atol=1e-3)
+    fp.vol.close()
+
+
+def run_reference_pipeline(sc, frames):
+    """launch_kernel (tsdf.cu:418-504) re-created from the verbatim kernels + verbatim filter_overlaps."""
+    import torch
+    from oracle import binding as ob
+    n = int(np.prod(sc.dims))
+    pad = 2 * sc.dims[1] * sc.dims[2] + 64
+    sdf = torch.full((n + 2 * pad,), float(sc.miu), dtype=torch.float32, device="cuda")
+    wt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    col = torch.zeros(n * 3, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros((n + 2 * pad) * sc.bins, dtype=torch.int32, device="cuda")
+    sdf_p, cnt_p = sdf.data_ptr() + pad * 4, cnt.data_ptr() + pad * sc.bins * 4
+    n_obs, num_objs = 0, 0
+    masks = []
+    for fr in frames:
+        mask = fr["mask"].copy()
+        E = fr["extrinsic"]
+        if n_obs > 0:
+            Rt, o = backproj_camera(E)
+            probs = torch.zeros(sc.H * sc.W * sc.bins, dtype=torch.float32, device="cuda")
+            box = torch.zeros(sc.H * sc.W * sc.bins, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            ob.ref_back_proj(sc.bins, sc.Kinv, Rt, o, sc.start, sc.end, sc.voxel, sc.dims, sdf_p, cnt_p, sc.W, sc.H,
+                             probs.data_ptr(), box.data_ptr())
+            mask, num_objs = ob.ref_filter_overlaps(probs.cpu().numpy(), mask, box.cpu().numpy(), sc.bins, n_obs, num_objs)
+        else:
+            num_objs = int(mask.max()) + 1
+        masks.append(mask)
+        d = torch.from_numpy(fr["depth"].view(np.int16)).cuda()
+        c = torch.from_numpy(fr["color"]).cuda()
+        m = torch.from_numpy(mask).cuda()
+        torch.cuda.synchronize()
+        ob.ref_integrate(sc.bins, sdf_p, col.data_ptr(), cnt_p, wt.data_ptr(), sc.dims, sc.start, sc.voxel,
+                         float(sc.miu), sc.K, d.data_ptr(), c.data_ptr(), m.data_ptr(), E, sc.W, sc.H)
+        n_obs += 1
+    sh = sc.dims
+    planes = {"sdf": sdf[pad:pad + n].cpu().numpy().reshape(sh), "weight": wt.cpu().numpy().reshape(sh),
+              "color": col.cpu().numpy().reshape(sh + (3,)),
+              "hist": cnt[pad * sc.bins:(pad + n) * sc.bins].cpu().numpy().view(np.uint32).reshape(sh + (sc.bins,))}
+    return planes, masks, num_objs
+
+
+@pytest.mark.parametrize("bins,ninst", [(32, 6), (16, 4)])
+def test_fuse_frame_pipeline_matches_reference(bins, ninst):
+    """Full labelled fusion: per-frame relabelled masks, num_objs and all planes == the reference pipeline."""
+    from oracle import binding as ob
+    if not ob.ref_available(bins):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=(64, 64, 64), bins=bins, n_instances=ninst, frames=6, yaw_step_deg=2.0, permute=True)
+    ref_planes, ref_masks, ref_num = run_reference_pipeline(sc, sc.frames)
+    v = sc.make_volume()
+    margins = []
+    for i, fr in enumerate(sc.frames):
+        mask = fr["mask"].copy()
+        v.fuse_frame(fr["depth"], fr["color"], mask, fr["extrinsic"])
+        if i > 0:
+            margins.append(v.last_merge().margin)
+        same = mask == ref_masks[i]
+        assert same.all(), f"frame {i}: relabelled mask differs at {int((~same).sum())} pixels (margins {margins})"
+    assert v.info().num_objs == ref_num
+    for k in ("sdf", "weight", "color", "hist"):
+        a, b = v.download(k), ref_planes[k]
+        same = (bits(a) == bits(b)) if k == "sdf" else (a == b)
+        assert same.all(), f"plane {k} differs at {int((~same).sum())} entries"
+    assert min(margins) > 1e-4, f"decision margins too small for a meaningful parity claim: {margins}"
+    v.close()
+
+
+@pytest.mark.parametrize("angle", [0.05, 0.6])
+def test_raycast_matches_reference_kernel(angle):
+    import torch
+    from oracle import binding as ob
+    from slam_maskrcnn_b200 import orbit_camera, palette
+    bins = 32
+    if not ob.ref_available(bins):
+        pytest.skip("oracle/_ref not built")
+    sc = Scenario(dims=(80, 80, 80), bins=bins, frames=6, yaw_step_deg=2.0)
+    fp = FusedPair(sc)
+    s2w, c = orbit_camera(sc.Kinv, angle, float(sc.mean_depth))
+    bgr, t, lab = fp.vol.raycast(s2w, c, want_t=True, want_label=True)
+    flags = fp.vol.ray_flags()
+    out = torch.zeros(sc.H * sc.W * 3, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ob.ref_show(bins, s2w, c, sc.start, sc.end, sc.voxel, sc.dims, fp.sdf_ptr, fp.col_ptr, fp.cnt_ptr, sc.W, sc.H,
+                out.data_ptr(), palette(bins))
+    ref = out.cpu().numpy().reshape(sc.H, sc.W, 3)
+    ok = flags == 0
+    assert ok.mean() > 0.9
+    assert (lab > 0).mean() > 0.02, "some instance surface should be visible"
+    assert (bgr[ok] == ref[ok]).all(), f"ray-cast image differs on {int((bgr[ok] != ref[ok]).any(-1).sum())} in-bounds rays"
+    fp.vol.close()
+
+
+def test_raycast_close_to_cpu_oracle():
+    """CPU restatement is tolerance-level for ray directions (MUFU.RSQ is approximate): labels agree on >= 99 %."""
+    from slam_maskrcnn_b200 import orbit_camera, palette
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=5, yaw_step_deg=2.0)
+    v = sc.make_volume()
+    cv = sc.make_cpu_volume()
+    for fr in sc.frames:
+        v.integrate_raw(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"])
+        cv.integrate(sc.K, fr["depth"], fr["color"], fr["gt"], fr["extrinsic"], sc.W, sc.H)
+    s2w, c = orbit_camera(sc.Kinv, 0.3, float(sc.mean_depth))
+    bgr, t, lab = v.raycast(s2w, c, want_t=True, want_label=True)
+    obgr, ot, olab = cv.raycast(s2w, c, sc.W, sc.H, palette(16))
+    assert (lab == olab).mean() > 0.99
+    both = (t > 0) & (ot > 0)
+    assert both.mean() > 0.3
+    np.testing.assert_allclose(t[both], ot[both], rtol=1e-3)
+    v.close()
