@@ -14,7 +14,8 @@ The reference as shipped does not compile here (every TU includes <opencv2/openc
 tsdf.cuh:2 / utils.cuh:3, and OpenCV C++ is absent), and its build/Makefile links OpenCV, so
 the build system itself is not run; only the self-contained line ranges above are compiled,
 with the Makefile's flags (nvcc -std=c++11 -dc, default -fmad=true -prec-div=true) plus
--gencode arch=compute_100a,code=sm_100a.  The extracted text lives only in a temporary
+-gencode arch=compute_100a,code=sm_100a and -maxrregcount=64 (needed for the reference's own
+1024-thread launches to fit the register file; allocation only, arithmetic unchanged).  The extracted text lives only in a temporary
 directory; nothing but the .so files is written to oracle/_ref/ (git-ignored, travels to
 the GPU box).  No reference source is copied into the repository.
 """
@@ -115,8 +116,12 @@ def build(bins_list=BINS, verbose=True):
                 with open(os.path.join(tmp, name), "w") as f:
                     f.write(text)
             shutil.copy(os.path.join(HERE, "ref_shim.cu"), os.path.join(tmp, "ref_shim.cu"))
-            common = ["nvcc", "-std=c++11", "-dc", "-Xcompiler", "-fPIC", "-w", f"-DMAX_OBJECTS={bins}",
-                      f"-I{REF}"] + ARCH
+            # -maxrregcount=64: the reference launches its ray kernels with 32x32 = 1024-thread blocks
+            # (tsdf.cu:441, viewer.cu:152), which needs <= 64 registers/thread; with separate
+            # compilation nvcc 12.9 allocates 108 for sm_100a and the verbatim launch fails with "too
+            # many resources requested".  The cap changes register allocation only, not arithmetic.
+            common = ["nvcc", "-std=c++11", "-dc", "-maxrregcount=64", "-Xcompiler", "-fPIC", "-w",
+                      f"-DMAX_OBJECTS={bins}", f"-I{REF}"] + ARCH
             objs = []
             for name in list(tu) + ["ref_shim.cu"]:
                 run(common + [name, "-o", name + ".o"], tmp)
