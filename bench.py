@@ -96,10 +96,10 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in names.items() if seen & b], "samples_under_load": len(busy)}
 
 
-def make_frames(n_pool, dims):
+def make_frames(n_pool, dims, hole_model="tum"):
     """A pool of distinct synthetic frames (cycled over the steps) + the volume placement."""
     from slam_maskrcnn_b200 import synth
-    sc = synth.SynthScene(n_instances=N_INSTANCES, seed=0, yaw_step_deg=2.0, permute=True)
+    sc = synth.SynthScene(n_instances=N_INSTANCES, seed=0, yaw_step_deg=2.0, permute=True, hole_model=hole_model)
     K = synth.intrinsic_matrix()
     Kinv = synth.intrinsic_inverse(K)
     f0 = sc.frame(0)
@@ -212,7 +212,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     dims = dims_for(args.gpus)
-    sc, K, Kinv, place, frames = make_frames(4, dims)
+    sc, K, Kinv, place, frames = make_frames(4, dims, args.hole_model)
     x_planes = 4
     # warm-up
     for _ in range(max(args.warmup, 0)):
@@ -268,7 +268,7 @@ def run_ours(args):
     slab = (rank * nz, nz)
     K_steps, W_steps = args.steps, max(args.warmup, 3)
     n_pool = min(args.pool, K_steps + W_steps)
-    sc, K, Kinv, place, frames = make_frames(n_pool, dims)
+    sc, K, Kinv, place, frames = make_frames(n_pool, dims, args.hole_model)
     vol = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=slab,
                  flags=args.flags)
     stream = torch.cuda.current_stream()
@@ -436,6 +436,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, dims), "dims": list(dims), "bins": bins,
                        "voxels_per_gpu": n_vox_rank, "frame_pool": n_pool,
+                       "invalid_depth_model": args.hole_model + (" (15 % invalid pixels, spatially clustered like the TUM fr2 frames the reference ships)"
+                                                                 if args.hole_model == "tum" else " (15 % independent per-pixel holes)"),
                        "l2": "no flush: each step reads and writes ~0.25 GB of voxel planes out of a >40 GB working set (> 126 MB L2)",
                        "frames_resident": "HBM (rank 0), NCCL broadcast inside each step" if world > 1 else "HBM"},
             "touched_voxel_updates_per_s": U_all / (t_dev_ms * 1e-3),
@@ -474,6 +476,7 @@ def main():
     ap.add_argument("--bins", type=int, default=80)
     ap.add_argument("--pool", type=int, default=12, help="distinct synthetic frames cycled over the steps")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--hole-model", default="tum", choices=["tum", "salt"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-merge", action="store_true")
     args = ap.parse_args()

@@ -1,51 +1,67 @@
 // k_integrate.cuh -- K0 (frame prep) and K1 (TSDF integrate) for sm_100a.
 //
 // K1 replaces tsdf_kernel (reference src/SfM_CUDA/tsdf.cu:18-70).  Design, B200-first:
-//   * one lane owns VEC consecutive z voxels of one (x,y) column; 32/VEC lanes cover a 32-voxel
-//     (128 B) run of the column, so every warp request on the SDF / weight planes is made of
-//     full 128 B lines moved with 128-bit loads/stores (the reference strides lanes along x,
-//     the slowest axis -- 32 lines per request);
-//   * the warp marches z in 32-voxel chunks; the z-invariant part of the pose transform
-//     (fma(px,r0,py*r1), bit-identical to the reference's evaluation order) is
-//     computed once per column and reused;
-//   * before touching a chunk ("brick" = CPW columns x 32 z), the warp runs an exact-conservative
-//     cull: the brick's 4 corners are projected, and the brick is skipped when every voxel in it
-//     provably fails the reference's own tests (outside the image, all-invalid depth, or behind
-//     the surface by more than miu against the per-tile max depth).  Skipped voxels would have
-//     early-outed in the reference, so results are identical; SFM_FLAG_NO_CULL disables it;
-//   * per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
-//     shuffles + one spread atomic per block -- they define the algorithmic bytes of the step.
+//
+//   * Work item = brick: CPW columns (consecutive y) x 32 consecutive z voxels at one x.  In the
+//     reference layout (z fastest) a brick is CPW full 128 B lines of each plane.
+//   * Stage A (classify): each of the 32 lanes of a warp classifies ONE brick by projecting its
+//     4 corners and querying two per-frame 8x8-pixel tile grids (max depth, min depth with
+//     invalid = 0) built by K0:
+//        CULL   every voxel provably fails the reference's own tests (outside the image, only
+//               invalid depth under it, or behind the surface band: cz - depth >= miu);
+//        FREE   every voxel provably lands inside the image on a valid pixel and in front of the
+//               surface band (depth - cz > miu), i.e. the reference computes diff = miu/miu = 1
+//               for all of them: no per-voxel projection is needed at all;
+//        MIXED  anything else: per-voxel evaluation, bit-identical to the reference.
+//     The tests are conservative with an explicit rounding-error budget, so results never change
+//     (SFM_FLAG_NO_CULL forces every brick to MIXED; the parity tests compare both).
+//   * Stage B (update): the warp walks the non-CULL bricks found by two ballots.  One lane owns
+//     VEC=4 consecutive z voxels of one column: SDF / weight move as 128-bit loads and stores, a
+//     warp request is CPW full lines.  The z-invariant part of the pose transform
+//     (fma(px,r0,py*r1), the order the reference's SASS uses) is hoisted per column.
+//   * Exact shortcuts: diff clamped to miu gives exactly 1.0f; (1.0f*w + 1.0f)/(w+1) is exactly
+//     1.0f; an SDF quad whose bits did not change is not written back.
+//   * Per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
+//     shuffles + one spread atomic pair per block -- they define the algorithmic bytes of the step.
 #pragma once
 #include "sfm_device.cuh"
 
 namespace sfm {
 
 // ---------------------------------------------------------------------------------------------
-// K0: per-frame prep.  One warp per kTile x kTile tile: max depth of the tile (for culling) and
-// max label (labels >= bins are a contract violation).
+// K0: per-frame prep.  One warp per kTile x kTile tile: max depth, min depth (invalid pixels
+// count as 0, so min > 0 <=> the tile has no hole), depth in metres as f32 (the reference's
+// depth/5000.f, IEEE divide, tsdf.cu:49) and max label (labels >= bins are a contract violation,
+// SURVEY appendix B.2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restrict__ depth,
-	const uint8_t *__restrict__ mask, int W, int H, int TW, int TH, int bins,
-	uint16_t *__restrict__ tilemax, unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
+	const uint8_t *__restrict__ mask, int W, int H, int TW, int TH, int bins, float depth_scale,
+	uint16_t *__restrict__ tilemax, uint16_t *__restrict__ tilemin, float *__restrict__ depth_m,
+	uint32_t *__restrict__ err)
 {
 	const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int warp = gtid >> 5, lane = threadIdx.x & 31;
 	if (warp >= TW * TH) return;
 	const int ty = warp / TW, tx = warp % TW;
-	unsigned dmax = 0, lmax = 0;
+	unsigned dmax = 0, dmin = 0xffffu, lmax = 0;
 #pragma unroll
 	for (int k = 0; k < 2; k++) {
 		const int r = (lane >> 2), c = ((lane & 3) << 1) + k;
 		const int y = ty * kTile + r, x = tx * kTile + c;
 		if (x < W && y < H) {
-			dmax = max(dmax, (unsigned)depth[y * W + x]);
+			const unsigned d = depth[y * W + x];
+			dmax = max(dmax, d);
+			dmin = min(dmin, d);
+			depth_m[y * W + x] = __fdiv_rn((float)d, depth_scale);
 			if (mask) lmax = max(lmax, (unsigned)mask[y * W + x]);
 		}
 	}
 	dmax = __reduce_max_sync(0xffffffffu, dmax);
+	dmin = __reduce_min_sync(0xffffffffu, dmin);
 	lmax = __reduce_max_sync(0xffffffffu, lmax);
 	if (lane == 0) {
 		tilemax[ty * TW + tx] = (uint16_t)dmax;
+		tilemin[ty * TW + tx] = (uint16_t)dmin;
 		if (bins > 0 && (int)lmax >= bins) atomicOr(err, 1u);
 	}
 }
@@ -77,14 +93,21 @@ __device__ __forceinline__ VoxelEval eval_voxel(const FrameView &f, const VolGeo
 	const int ix = __float2int_rd(sx), iy = __float2int_rd(sy);
 	if (ix < 0 || ix >= f.W || iy < 0 || iy >= f.H) return r;
 	const int img = iy * f.W + ix;
-	const unsigned d = __ldg(f.depth + img);
-	if (d == 0) return r;
-	float diff = __fadd_rn(__fdiv_rn((float)d, f.depth_scale), -cz);
+	const float dm = __ldg(f.depth_m + img);  // = depth/5000.f, IEEE divide done once per pixel in K0
+	if (dm == 0.f) return r;                  // depth == 0  (depth >= 1 gives dm > 0)
+	float diff = __fadd_rn(dm, -cz);
 	if (diff <= -g.miu) return r;  // NaN survives, as in the reference
-	if (diff > g.miu) diff = g.miu;
-	r.diff = __fdiv_rn(diff, g.miu);
+	// tsdf.cu:51-52: clamp, then diff/miu.  miu/miu == 1.0f exactly, so the clamped case needs no divide.
+	r.diff = (diff > g.miu) ? 1.0f : __fdiv_rn(diff, g.miu);
 	r.img = img;
 	return r;
+}
+
+// tsdf.cu:56  (sdf*w + diff)/(w+1)  -> FFMA, IEEE divide.  (1.0f*w + 1.0f)/(w+1) is exactly 1.0f
+// for 0 <= w < 2^24 (both the fma and the quotient are exact), so that case skips the divide.
+__device__ __forceinline__ float sdf_update(float s, int w, float diff) {
+	if (s == 1.0f && diff == 1.0f && (unsigned)w < (1u << 24)) return 1.0f;
+	return __fdiv_rn(__fmaf_rn(s, (float)w, diff), (float)(w + 1));
 }
 
 // colour running mean + histogram increment (tsdf.cu:57-62) for one near-surface voxel
@@ -105,133 +128,174 @@ __device__ __forceinline__ void update_surface_voxel(const Planes &p, const Fram
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using F = float4; using I = int4; };
-template <> struct VecT<2> { using F = float2; using I = int2; };
 template <> struct VecT<1> { using F = float; using I = int; };
+
+__device__ __forceinline__ bool same_bits(const float4 &a, const float4 &b) {
+	return __float_as_uint(a.x) == __float_as_uint(b.x) && __float_as_uint(a.y) == __float_as_uint(b.y) &&
+		__float_as_uint(a.z) == __float_as_uint(b.z) && __float_as_uint(a.w) == __float_as_uint(b.w);
+}
+__device__ __forceinline__ bool same_bits(const float &a, const float &b) {
+	return __float_as_uint(a) == __float_as_uint(b);
+}
+
+enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
+
+// Stage A: classify one brick (x, columns y0..ylast, local z zc0..zc1).
+__device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, int x, int y0, int ylast,
+	int zc0, int zc1)
+{
+	const float px = __fmaf_rn((float)x, g.vx, g.sx);
+	float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+	float szmin = INFINITY, szmax = -INFINITY, czmin = INFINITY, czmax = -INFINITY, scale_c = 0.f;
+#pragma unroll
+	for (int corner = 0; corner < 4; corner++) {
+		const float py = __fmaf_rn((float)((corner & 1) ? ylast : y0), g.vy, g.sy);
+		const float pz = __fmaf_rn((float)(g.z0 + ((corner & 2) ? zc1 : zc0)), g.vz, g.sz);
+		const float cx = affine_finish(affine_hoist(px, py, f.E[0], f.E[1]), pz, f.E[2], f.E[3]);
+		const float cy = affine_finish(affine_hoist(px, py, f.E[4], f.E[5]), pz, f.E[6], f.E[7]);
+		const float cz = affine_finish(affine_hoist(px, py, f.E[8], f.E[9]), pz, f.E[10], f.E[11]);
+		const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
+		const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
+		const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
+		const float u = sx / sz, v = sy / sz;
+		umin = fminf(umin, u); umax = fmaxf(umax, u);
+		vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+		szmin = fminf(szmin, sz); szmax = fmaxf(szmax, sz);
+		czmin = fminf(czmin, cz); czmax = fmaxf(czmax, cz);
+		// magnitude bound of the camera-space coordinates (rounding-error budget)
+		scale_c = fmaxf(scale_c, f.cull_lin * (fabsf(px) + fabsf(py) + fabsf(pz) + 1.f) + f.cull_t);
+	}
+	// The projective map is monotone along any segment that stays on one side of the camera plane,
+	// so with all four corners strictly on one side the pixel coordinates of every voxel of the
+	// brick lie inside the corner bounding box (plus rounding slack).  Rounding-error budget:
+	// |c*| <= scale_c, per-voxel error of c*, s* ~ 1e-6*scale; a brick is only classified when all
+	// corners are at least 1e-2*scale_sz away from the camera plane, which bounds the per-voxel
+	// pixel error by ~1e-4*(Krow/K2row + |u|) -- the slack is 10x that.  NaNs fail `finite`.
+	const float zguard = 1e-2f * f.cull_k2 * scale_c;
+	const bool one_side = (szmin > zguard) || (szmax < -zguard);
+	const bool finite = fabsf(umin) < 1e8f && fabsf(umax) < 1e8f && fabsf(vmin) < 1e8f && fabsf(vmax) < 1e8f &&
+		fabsf(czmin) < 1e30f && fabsf(czmax) < 1e30f;
+	if (!(one_side && finite)) return kMixed;
+	const float slack_u = f.cull_slack0 + 1e-3f * fmaxf(fabsf(umin), fabsf(umax));
+	const float slack_v = f.cull_slack0 + 1e-3f * fmaxf(fabsf(vmin), fabsf(vmax));
+	const float ulo = umin - slack_u, uhi = umax + slack_u;
+	const float vlo = vmin - slack_v, vhi = vmax + slack_v;
+	if (uhi < 0.f || ulo >= (float)f.W || vhi < 0.f || vlo >= (float)f.H) return kCull;  // outside the image
+	const bool inside = ulo >= 0.f && uhi < (float)f.W && vlo >= 0.f && vhi < (float)f.H;
+	const int tx0 = max(0, (int)floorf(ulo)) / kTile, tx1 = min(f.W - 1, (int)floorf(uhi)) / kTile;
+	const int ty0 = max(0, (int)floorf(vlo)) / kTile, ty1 = min(f.H - 1, (int)floorf(vhi)) / kTile;
+	if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 96) return kMixed;  // huge footprint (brick close to the camera)
+	unsigned dmax = 0, dmin = 0xffffu;
+	for (int ty = ty0; ty <= ty1; ty++)
+		for (int tx = tx0; tx <= tx1; tx++) {
+			dmax = max(dmax, (unsigned)__ldg(f.tilemax + ty * f.TW + tx));
+			dmin = min(dmin, (unsigned)__ldg(f.tilemin + ty * f.TW + tx));
+		}
+	if (dmax == 0) return kCull;  // only invalid depth under the brick
+	if (szmin > 0.f) {
+		const float dmax_m = __fdiv_rn((float)dmax, f.depth_scale), dmin_m = __fdiv_rn((float)dmin, f.depth_scale);
+		const float eps = 1e-4f * (scale_c + dmax_m);
+		// every voxel: diff = d/scale - cz <= dmax/scale - czmin + eps  =>  behind the surface band
+		if (czmin - dmax_m >= g.miu + eps) return kCull;
+		// every voxel: valid pixel inside the image and diff >= dmin/scale - czmax - eps > miu
+		if (inside && dmin > 0 && dmin_m - czmax > g.miu + eps) return kFree;
+	}
+	return kMixed;
+}
 
 template <int VEC, bool LABELS, bool CULL>
 __global__ void __launch_bounds__(256) integrate_kernel(Planes p, VolGeom g, FrameView f,
 	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
 {
 	constexpr int LPC = 32 / VEC;  // lanes per column
-	constexpr int CPW = 32 / LPC;  // columns per warp
+	constexpr int CPW = 32 / LPC;  // columns per brick
+	using F = typename VecT<VEC>::F;
+	using I = typename VecT<VEC>::I;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int zq = lane % LPC, ci = lane / LPC;
+	const int nchunks = (g.nz + 31) >> 5;
 	const int groups_per_x = (g.Dy + CPW - 1) / CPW;
-	const long long group = (long long)blockIdx.x * 8 + warp;
+	const long long nbricks = (long long)g.Dx * groups_per_x * nchunks;
+	const long long warp_base = ((long long)blockIdx.x * 8 + warp) * 32;
 	unsigned nU = 0, nS = 0;
-	if (group < (long long)g.Dx * groups_per_x) {
-		const int x = (int)(group / groups_per_x);
-		const int y0 = (int)(group % groups_per_x) * CPW;
-		const int y = y0 + ci;
-		const bool col_ok = y < g.Dy;
+
+	// ---- stage A: lane-parallel classification of 32 bricks --------------------------------
+	int cls = kCull;
+	int bx = 0, by0 = 0, bzc = 0;
+	{
+		const long long b = warp_base + lane;
+		if (b < nbricks) {
+			bzc = (int)(b % nchunks) << 5;
+			const long long t = b / nchunks;
+			by0 = (int)(t % groups_per_x) * CPW;
+			bx = (int)(t / groups_per_x);
+			cls = CULL ? classify_brick(f, g, bx, by0, min(by0 + CPW - 1, g.Dy - 1), bzc, min(bzc + 31, g.nz - 1)) : kMixed;
+		}
+	}
+	const unsigned free_mask = __ballot_sync(0xffffffffu, cls == kFree);
+	unsigned todo = __ballot_sync(0xffffffffu, cls != kCull);
+
+	// ---- stage B: cooperative update of the surviving bricks --------------------------------
+	while (todo) {
+		const int s = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const int x = __shfl_sync(0xffffffffu, bx, s);
+		const int y = __shfl_sync(0xffffffffu, by0, s) + ci;
+		const int zl = __shfl_sync(0xffffffffu, bzc, s) + zq * VEC;
+		if (y >= g.Dy || zl >= g.nz) continue;
+		const size_t v0 = ((size_t)x * g.Dy + y) * (size_t)g.nz + zl;
+		if ((free_mask >> s) & 1u) {
+			// FREE brick: every voxel gets diff == 1.0f (> near_gate, so no colour / histogram update)
+			const F sv = *reinterpret_cast<const F *>(p.sdf + v0);
+			I wv = *reinterpret_cast<const I *>(p.wt + v0);
+			F sn = sv;
+			float *sp = reinterpret_cast<float *>(&sn);
+			int *w = reinterpret_cast<int *>(&wv);
+#pragma unroll
+			for (int k = 0; k < VEC; k++) {
+				sp[k] = sdf_update(sp[k], w[k], 1.0f);
+				w[k] += 1;
+			}
+			nU += VEC;
+			*reinterpret_cast<I *>(p.wt + v0) = wv;
+			if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
+			continue;
+		}
+		// MIXED brick: per-voxel evaluation
 		const float px = __fmaf_rn((float)x, g.vx, g.sx);
 		const float py = __fmaf_rn((float)y, g.vy, g.sy);
 		const float h0 = affine_hoist(px, py, f.E[0], f.E[1]);
 		const float h1 = affine_hoist(px, py, f.E[4], f.E[5]);
 		const float h2 = affine_hoist(px, py, f.E[8], f.E[9]);
-		const size_t colbase = ((size_t)x * g.Dy + (col_ok ? y : 0)) * (size_t)g.nz;
-
-		// corner assignment for the cull test: lane&1 -> y end, lane&2 -> z end
-		const int ylast = min(y0 + CPW - 1, g.Dy - 1);
-		const float cpy = __fmaf_rn((float)((lane & 1) ? ylast : y0), g.vy, g.sy);
-		const float c0 = affine_hoist(px, cpy, f.E[0], f.E[1]);
-		const float c1 = affine_hoist(px, cpy, f.E[4], f.E[5]);
-		const float c2 = affine_hoist(px, cpy, f.E[8], f.E[9]);
-
-		for (int zc = 0; zc < g.nz; zc += 32) {
-			if (CULL) {
-				const int zl_end = min(zc + 31, g.nz - 1);
-				const float cpz = __fmaf_rn((float)(g.z0 + ((lane & 2) ? zl_end : zc)), g.vz, g.sz);
-				const float ccx = affine_finish(c0, cpz, f.E[2], f.E[3]);
-				const float ccy = affine_finish(c1, cpz, f.E[6], f.E[7]);
-				const float ccz = affine_finish(c2, cpz, f.E[10], f.E[11]);
-				const float ssx = dot3_ref(f.K[0], f.K[1], f.K[2], ccx, ccy, ccz);
-				const float ssy = dot3_ref(f.K[3], f.K[4], f.K[5], ccx, ccy, ccz);
-				const float ssz = dot3_ref(f.K[6], f.K[7], f.K[8], ccx, ccy, ccz);
-				const float u = ssx / ssz, vv = ssy / ssz;
-				// reduce over the 4 corners (lanes differing in bits 0,1); all groups of 4 are identical
-				float umin = u, umax = u, vmin = vv, vmax = vv, szmin = ssz, szmax = ssz, czmin = ccz;
-				// magnitude bound of the camera-space coordinates of this brick (rounding-error budget)
-				float scale_c = f.cull_lin * (fabsf(px) + fabsf(cpy) + fabsf(cpz) + 1.f) + f.cull_t;
+		VoxelEval ev[VEC];
+		bool any = false;
 #pragma unroll
-				for (int o = 1; o <= 2; o <<= 1) {
-					umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-					umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-					vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-					vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-					szmin = fminf(szmin, __shfl_xor_sync(0xffffffffu, szmin, o));
-					szmax = fmaxf(szmax, __shfl_xor_sync(0xffffffffu, szmax, o));
-					czmin = fminf(czmin, __shfl_xor_sync(0xffffffffu, czmin, o));
-					scale_c = fmaxf(scale_c, __shfl_xor_sync(0xffffffffu, scale_c, o));
-				}
-				// The projective map is monotone along any segment that stays on one side of the
-				// camera plane, so with all four corners strictly on one side the pixel coordinates of
-				// every voxel of the brick lie inside the corner bounding box (plus rounding slack).
-				// Rounding-error budget: |c*| <= scale_c, per-voxel error of c*, s* ~ 1e-6 * scale; a brick
-				// is only culled when all corners are at least 1e-2*scale_sz away from the camera plane,
-				// which bounds the per-voxel pixel error by ~1e-4*(Krow/K2row + |u|) -- slack is 10x that.
-				const float zguard = 1e-2f * f.cull_k2 * scale_c;
-				const bool one_side = (szmin > zguard) || (szmax < -zguard);
-				const bool finite = (umin == umin) && (umax == umax) && (vmin == vmin) && (vmax == vmax) &&
-					fabsf(umin) < 1e8f && fabsf(umax) < 1e8f && fabsf(vmin) < 1e8f && fabsf(vmax) < 1e8f;
-				if (one_side && finite) {
-					const float slack_u = f.cull_slack0 + 1e-3f * fmaxf(fabsf(umin), fabsf(umax));
-					const float slack_v = f.cull_slack0 + 1e-3f * fmaxf(fabsf(vmin), fabsf(vmax));
-					const float ulo = umin - slack_u, uhi = umax + slack_u;
-					const float vlo = vmin - slack_v, vhi = vmax + slack_v;
-					if (uhi < 0.f || ulo >= (float)f.W || vhi < 0.f || vlo >= (float)f.H) continue;  // outside the image
-					// pixel bbox -> tile range
-					const int tx0 = max(0, (int)floorf(ulo)) / kTile, tx1 = min(f.W - 1, (int)floorf(uhi)) / kTile;
-					const int ty0 = max(0, (int)floorf(vlo)) / kTile, ty1 = min(f.H - 1, (int)floorf(vhi)) / kTile;
-					const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
-					const int cnt = nx * ny;
-					if (cnt <= 512) {
-						unsigned dmax = 0;
-						for (int i = lane; i < cnt; i += 32)
-							dmax = max(dmax, (unsigned)__ldg(f.tilemax + (ty0 + i / nx) * f.TW + tx0 + i % nx));
-						dmax = __reduce_max_sync(0xffffffffu, dmax);
-						if (dmax == 0) continue;  // only invalid depth under the brick
-						if (szmin > 0.f) {
-							// every voxel: diff = d/scale - cz <= dmax/scale - czmin + eps
-							const float dmax_m = __fdiv_rn((float)dmax, f.depth_scale);
-							const float eps = 1e-4f * (scale_c + dmax_m);
-							if (czmin - dmax_m >= g.miu + eps) continue;  // wholly behind the surface band
-						}
-					}
-				}
-			}
-			const int zl = zc + zq * VEC;
-			if (!col_ok || zl >= g.nz) continue;
-			VoxelEval ev[VEC];
-			bool any = false;
-#pragma unroll
-			for (int k = 0; k < VEC; k++) {
-				ev[k] = eval_voxel(f, g, h0, h1, h2, g.z0 + zl + k);
-				any |= ev[k].img >= 0;
-			}
-			if (!any) continue;
-			const size_t v0 = colbase + zl;
-			typename VecT<VEC>::F sv = *reinterpret_cast<const typename VecT<VEC>::F *>(p.sdf + v0);
-			typename VecT<VEC>::I wv = *reinterpret_cast<const typename VecT<VEC>::I *>(p.wt + v0);
-			float *s = reinterpret_cast<float *>(&sv);
-			int *w = reinterpret_cast<int *>(&wv);
-#pragma unroll
-			for (int k = 0; k < VEC; k++) {
-				if (ev[k].img < 0) continue;
-				const int wk = w[k];
-				// tsdf.cu:56  (sdf*w + diff) / (w + 1)   -> FFMA, IEEE divide
-				s[k] = __fdiv_rn(__fmaf_rn(s[k], (float)wk, ev[k].diff), (float)(wk + 1));
-				if (ev[k].diff < f.near_gate) {  // tsdf.cu:57-62
-					update_surface_voxel<LABELS>(p, f, v0 + k, wk, ev[k].img, err);
-					nS++;
-				}
-				w[k] = wk + 1;  // tsdf.cu:68
-				nU++;
-			}
-			*reinterpret_cast<typename VecT<VEC>::F *>(p.sdf + v0) = sv;
-			*reinterpret_cast<typename VecT<VEC>::I *>(p.wt + v0) = wv;
+		for (int k = 0; k < VEC; k++) {
+			ev[k] = eval_voxel(f, g, h0, h1, h2, g.z0 + zl + k);
+			any |= ev[k].img >= 0;
 		}
+		if (!any) continue;
+		const F sv = *reinterpret_cast<const F *>(p.sdf + v0);
+		I wv = *reinterpret_cast<const I *>(p.wt + v0);
+		F sn = sv;
+		float *sp = reinterpret_cast<float *>(&sn);
+		int *w = reinterpret_cast<int *>(&wv);
+#pragma unroll
+		for (int k = 0; k < VEC; k++) {
+			if (ev[k].img < 0) continue;
+			const int wk = w[k];
+			sp[k] = sdf_update(sp[k], wk, ev[k].diff);
+			if (ev[k].diff < f.near_gate) {  // tsdf.cu:57-62
+				update_surface_voxel<LABELS>(p, f, v0 + k, wk, ev[k].img, err);
+				nS++;
+			}
+			w[k] = wk + 1;  // tsdf.cu:68
+			nU++;
+		}
+		*reinterpret_cast<I *>(p.wt + v0) = wv;
+		if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 	}
+
 	// fold U / S: warp shuffle -> shared -> one spread atomic pair per block
 	nU = __reduce_add_sync(0xffffffffu, nU);
 	nS = __reduce_add_sync(0xffffffffu, nS);

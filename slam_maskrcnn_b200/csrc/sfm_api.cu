@@ -99,7 +99,8 @@ struct sfm_volume {
 	// frame staging (device)
 	uint16_t *d_depth = nullptr;
 	uint8_t *d_rgb = nullptr, *d_mask = nullptr;
-	uint16_t *d_tilemax = nullptr;
+	uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;
+	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
 	uint32_t *d_err = nullptr;
 	uint8_t *d_palette = nullptr;
@@ -223,6 +224,8 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	f.rgb = (const uint8_t *)d_rgb;
 	f.mask = (const uint8_t *)d_mask;
 	f.tilemax = v->d_tilemax;
+	f.tilemin = v->d_tilemin;
+	f.depth_m = v->d_depth_m;
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
 	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
@@ -254,15 +257,15 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set (call sfm_set_bounds / sfm_init_from_frame / sfm_parse_frame first)");
 	const FrameView f = make_frame_view(v, d_depth, d_rgb, d_mask, E16);
 	const int prep_warps = v->TW * v->TH;
-	const int prep_blocks = std::max((prep_warps * 32 + 255) / 256, (2 * kStatSlots + 255) / 256);
+	const int prep_blocks = (prep_warps * 32 + 255) / 256;
 	prep_frame_kernel<<<prep_blocks, 256, 0, v->stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
-		v->bins, v->d_tilemax, v->d_stats, v->d_err);
+		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err);
 	LAUNCH_CHECK(v);
 	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	const int cpw = vec4 ? 4 : 1;
-	const long long groups = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw);
-	const int blocks = (int)((groups + 7) / 8);
+	const long long nbricks = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw) * ((v->g.nz + 31) / 32);
+	const int blocks = (int)((nbricks + 255) / 256);  // 8 warps x 32 bricks per block
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
 	if (vec4) {
@@ -582,6 +585,8 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->d_mask, npx));
 	CU_OR_DESTROY(cudaMemset(v->d_mask, 0, npx));
 	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, (size_t)v->TW * v->TH * 2));
+	CU_OR_DESTROY(cudaMalloc(&v->d_tilemin, (size_t)v->TW * v->TH * 2));
+	CU_OR_DESTROY(cudaMalloc(&v->d_depth_m, npx * 4));
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
@@ -615,7 +620,7 @@ void sfm_destroy(sfm_volume *v) {
 	cudaSetDevice(v->desc.device);
 	if (v->stream) cudaStreamSynchronize(v->stream);
 	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist);
-	cudaFree(v->d_depth); cudaFree(v->d_rgb); cudaFree(v->d_mask); cudaFree(v->d_tilemax); cudaFree(v->d_stats);
+	cudaFree(v->d_depth); cudaFree(v->d_rgb); cudaFree(v->d_mask); cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
 	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_fold);

@@ -53,13 +53,19 @@ def mean_depth(depth):
 
 class SynthScene:
     def __init__(self, n_instances=15, seed=0, width=W, height=H, intrinsics=(FX, FY, CX, CY),
-                 yaw_step_deg=0.1, hole_frac=0.15, flip_frac=0.05, min_pixels=2000, permute=True):
+                 yaw_step_deg=0.1, hole_frac=0.15, flip_frac=0.05, min_pixels=2000, permute=True,
+                 hole_model="tum"):
         self.K_inst = int(n_instances)
         self.W, self.H = int(width), int(height)
         self.fx, self.fy, self.cx, self.cy = [float(v) for v in intrinsics]
         self.yaw_step = np.deg2rad(yaw_step_deg)
         self.hole_frac, self.flip_frac, self.min_pixels = hole_frac, flip_frac, min_pixels
         self.permute = permute
+        # "tum": spatially clustered invalid depth (blobs + occlusion shadows + 0.5 % speckle), calibrated
+        #        to the two real TUM fr2 depth frames the reference ships (Mask_RCNN/samples/1311871965.993806.png:
+        #        15.5 % zeros, 77 % of 8x8 tiles hole-free, 12 % all-hole, 11 % mixed);
+        # "salt": independent per-pixel holes (SURVEY 8d's first-cut spec; unlike any real Kinect frame).
+        self.hole_model = hole_model
         rng = np.random.default_rng(seed)
         k = self.K_inst
         self.centers = np.stack([rng.uniform(-1.2, 1.2, k), rng.uniform(0.3, 0.9, k), rng.uniform(1.6, 3.1, k)], 1)
@@ -121,7 +127,7 @@ class SynthScene:
         rng = np.random.default_rng(1000 + f)
         depth = np.clip(best * 5000.0, 0, 65535).astype(np.uint16)
         depth[~np.isfinite(best)] = 0
-        depth[rng.random((self.H, self.W)) < self.hole_frac] = 0
+        depth[self.hole_mask(rng, inst, surf, best)] = 0
         base = np.where((inst > 0)[..., None], self.sphere_bgr[np.maximum(inst - 1, 0)], self.plane_bgr[np.maximum(surf, 0)])
         color = np.clip(base + rng.integers(-12, 13, base.shape), 0, 255).astype(np.uint8)
         # labels: drop small instances (dmask.py:34-45), permute ids per frame, flip 5 % of instance pixels
@@ -143,6 +149,30 @@ class SynthScene:
             "depth": depth, "color": color, "mask": mask.astype(np.uint8), "gt": gt.astype(np.uint8),
             "extrinsic": self.extrinsic(f), "pose": self.tum_pose(f),
         }
+
+
+def _hole_mask(self, rng, inst, surf, best=None):
+    if self.hole_frac <= 0:
+        return np.zeros((self.H, self.W), bool)
+    if self.hole_model == "salt":
+        return rng.random((self.H, self.W)) < self.hole_frac
+    from scipy import ndimage
+    scale = self.W / W
+    # occlusion shadows: a thin band of invalid depth on depth discontinuities (> 10 cm jumps)
+    edges = np.zeros((self.H, self.W), bool)
+    if best is not None:
+        z = np.where(np.isfinite(best), best, 0.0)
+        edges[:, 1:] |= np.abs(z[:, 1:] - z[:, :-1]) > 0.1
+        edges[1:, :] |= np.abs(z[1:, :] - z[:-1, :]) > 0.1
+    shadow = ndimage.binary_dilation(edges, iterations=1) if scale > 0.5 else edges
+    speckle = rng.random((self.H, self.W)) < 0.001
+    blob_frac = max(self.hole_frac - float(shadow.mean()) - 0.001, 0.0)
+    field = ndimage.gaussian_filter(rng.standard_normal((self.H, self.W)), sigma=28 * scale)
+    blobs = field > np.quantile(field, 1.0 - blob_frac) if blob_frac > 0 else np.zeros_like(shadow)
+    return shadow | speckle | blobs
+
+
+SynthScene.hole_mask = _hole_mask
 
 
 def small_scene(width=160, height=120, n_instances=6, **kw):
