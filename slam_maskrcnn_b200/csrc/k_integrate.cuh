@@ -22,7 +22,7 @@
 //   * Exact shortcuts: diff clamped to miu gives exactly 1.0f; (1.0f*w + 1.0f)/(w+1) is exactly
 //     1.0f; an SDF quad whose bits did not change is not written back.
 //   * Per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
-//     shuffles + one spread atomic pair per block -- they define the algorithmic bytes of the step.
+//     shuffles + one spread atomic pair per warp -- they define the algorithmic bytes of the step.
 #pragma once
 #include "sfm_device.cuh"
 
@@ -32,14 +32,15 @@ namespace sfm {
 // K0: per-frame prep.  One warp per kTile x kTile tile: max depth, min depth (invalid pixels
 // count as 0, so min > 0 <=> the tile has no hole), depth in metres as f32 (the reference's
 // depth/5000.f, IEEE divide, tsdf.cu:49) and max label (labels >= bins are a contract violation,
-// SURVEY appendix B.2).
+// SURVEY appendix B.2).  Also resets K1's dynamic work counter.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restrict__ depth,
 	const uint8_t *__restrict__ mask, int W, int H, int TW, int TH, int bins, float depth_scale,
 	uint16_t *__restrict__ tilemax, uint16_t *__restrict__ tilemin, float *__restrict__ depth_m,
-	uint32_t *__restrict__ err)
+	uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
 {
 	const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gtid == 0) *work_counter = 0u;  // K1's dynamic work counter
 	const int warp = gtid >> 5, lane = threadIdx.x & 31;
 	if (warp >= TW * TH) return;
 	const int ty = warp / TW, tx = warp % TW;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restr
 	lmax = __reduce_max_sync(0xffffffffu, lmax);
 	if (lane == 0) {
 		tilemax[ty * TW + tx] = (uint16_t)dmax;
-		tilemin[ty * TW + tx] = (uint16_t)dmin;
+		tilemin[ty * TW + tx] = (uint16_t)dmin;  // invalid pixels count as 0: min > 0 <=> no hole in the tile
 		if (bins > 0 && (int)lmax >= bins) atomicOr(err, 1u);
 	}
 }
@@ -157,7 +158,7 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 		const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
 		const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
 		const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
-		const float u = sx / sz, v = sy / sz;
+		const float u = __fdividef(sx, sz), v = __fdividef(sy, sz);  // approximate is fine: the slack is 1e-3 relative
 		umin = fminf(umin, u); umax = fmaxf(umax, u);
 		vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
 		szmin = fminf(szmin, sz); szmax = fmaxf(szmax, sz);
@@ -197,15 +198,18 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 		const float eps = 1e-4f * (scale_c + dmax_m);
 		// every voxel: diff = d/scale - cz <= dmax/scale - czmin + eps  =>  behind the surface band
 		if (czmin - dmax_m >= g.miu + eps) return kCull;
-		// every voxel: valid pixel inside the image and diff >= dmin/scale - czmax - eps > miu
+		// every voxel: valid pixel inside the image (no tile under the box has a hole: min > 0) and
+		// diff >= dmin/scale - czmax - eps > miu   =>  diff clamps to miu, i.e. exactly 1.0f
+		// (An exact per-pixel invalid bitmap was measured here: it lifts the FREE share from 15 % to
+		// 23 % of the surviving bricks but costs more instructions than it saves; see DESIGN.md.)
 		if (inside && dmin > 0 && dmin_m - czmax > g.miu + eps) return kFree;
 	}
 	return kMixed;
 }
 
 template <int VEC, bool LABELS, bool CULL>
-__global__ void __launch_bounds__(256) integrate_kernel(Planes p, VolGeom g, FrameView f,
-	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
+__global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, FrameView f,
+	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
 {
 	constexpr int LPC = 32 / VEC;  // lanes per column
 	constexpr int CPW = 32 / LPC;  // columns per brick
@@ -216,8 +220,17 @@ __global__ void __launch_bounds__(256) integrate_kernel(Planes p, VolGeom g, Fra
 	const int nchunks = (g.nz + 31) >> 5;
 	const int groups_per_x = (g.Dy + CPW - 1) / CPW;
 	const long long nbricks = (long long)g.Dx * groups_per_x * nchunks;
-	const long long warp_base = ((long long)blockIdx.x * 8 + warp) * 32;
+	// Persistent warps with dynamic work fetching: the grid is sized to fill the machine once and
+	// every warp pulls batches of 32 consecutive bricks from a global counter (reset by K0), so a
+	// warp that lands on culled space immediately moves on instead of idling in a resident block.
+	const long long nbatches = (nbricks + 31) >> 5;
 	unsigned nU = 0, nS = 0;
+	for (;;) {
+	long long batch = 0;
+	if (lane == 0) batch = atomicAdd(work_counter, 1u);
+	batch = __shfl_sync(0xffffffffu, batch, 0);
+	if (batch >= nbatches) break;
+	const long long warp_base = batch << 5;
 
 	// ---- stage A: lane-parallel classification of 32 bricks --------------------------------
 	int cls = kCull;
@@ -236,21 +249,39 @@ __global__ void __launch_bounds__(256) integrate_kernel(Planes p, VolGeom g, Fra
 	unsigned todo = __ballot_sync(0xffffffffu, cls != kCull);
 
 	// ---- stage B: cooperative update of the surviving bricks --------------------------------
+	// Software pipeline: the SDF / weight quads of brick i+1 are requested before brick i is
+	// evaluated, so every warp keeps two bricks' worth of 128-bit loads in flight.
+	F sv_n{}; I wv_n{};
+	size_t v_n = 0;
+	int x_n = 0, y_n = 0, zl_n = 0;
+	bool ok_n = false;
+	auto issue = [&](int s) {  // executed by all 32 lanes (full-mask shuffles)
+		x_n = __shfl_sync(0xffffffffu, bx, s);
+		y_n = __shfl_sync(0xffffffffu, by0, s) + ci;
+		zl_n = __shfl_sync(0xffffffffu, bzc, s) + zq * VEC;
+		ok_n = (y_n < g.Dy) && (zl_n < g.nz);
+		v_n = ((size_t)x_n * g.Dy + (ok_n ? y_n : 0)) * (size_t)g.nz + (ok_n ? zl_n : 0);
+		if (ok_n) {
+			sv_n = *reinterpret_cast<const F *>(p.sdf + v_n);
+			wv_n = *reinterpret_cast<const I *>(p.wt + v_n);
+		}
+	};
+	if (todo) issue(__ffs(todo) - 1);
 	while (todo) {
 		const int s = __ffs(todo) - 1;
 		todo &= todo - 1;
-		const int x = __shfl_sync(0xffffffffu, bx, s);
-		const int y = __shfl_sync(0xffffffffu, by0, s) + ci;
-		const int zl = __shfl_sync(0xffffffffu, bzc, s) + zq * VEC;
-		if (y >= g.Dy || zl >= g.nz) continue;
-		const size_t v0 = ((size_t)x * g.Dy + y) * (size_t)g.nz + zl;
+		const F sv = sv_n;
+		I wv = wv_n;
+		const size_t v0 = v_n;
+		const bool ok = ok_n;
+		const int x = x_n, y = y_n, zl = zl_n;
+		if (todo) issue(__ffs(todo) - 1);  // prefetch the next brick
+		if (!ok) continue;
+		F sn = sv;
+		float *sp = reinterpret_cast<float *>(&sn);
+		int *w = reinterpret_cast<int *>(&wv);
 		if ((free_mask >> s) & 1u) {
 			// FREE brick: every voxel gets diff == 1.0f (> near_gate, so no colour / histogram update)
-			const F sv = *reinterpret_cast<const F *>(p.sdf + v0);
-			I wv = *reinterpret_cast<const I *>(p.wt + v0);
-			F sn = sv;
-			float *sp = reinterpret_cast<float *>(&sn);
-			int *w = reinterpret_cast<int *>(&wv);
 #pragma unroll
 			for (int k = 0; k < VEC; k++) {
 				sp[k] = sdf_update(sp[k], w[k], 1.0f);
@@ -261,56 +292,111 @@ __global__ void __launch_bounds__(256) integrate_kernel(Planes p, VolGeom g, Fra
 			if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 			continue;
 		}
-		// MIXED brick: per-voxel evaluation
+		// MIXED brick: per-voxel evaluation (tsdf.cu:30-68), phased so that the independent loads of
+		// the lane's VEC voxels are in flight together instead of one dependent miss after another.
 		const float px = __fmaf_rn((float)x, g.vx, g.sx);
 		const float py = __fmaf_rn((float)y, g.vy, g.sy);
 		const float h0 = affine_hoist(px, py, f.E[0], f.E[1]);
 		const float h1 = affine_hoist(px, py, f.E[4], f.E[5]);
 		const float h2 = affine_hoist(px, py, f.E[8], f.E[9]);
-		VoxelEval ev[VEC];
-		bool any = false;
+		float czv[VEC];
+		int img[VEC];
+		bool inb[VEC];
+		// phase 1: projection -> pixel (no memory)
 #pragma unroll
 		for (int k = 0; k < VEC; k++) {
-			ev[k] = eval_voxel(f, g, h0, h1, h2, g.z0 + zl + k);
-			any |= ev[k].img >= 0;
+			const float pz = __fmaf_rn((float)(g.z0 + zl + k), g.vz, g.sz);
+			const float cx = affine_finish(h0, pz, f.E[2], f.E[3]);
+			const float cy = affine_finish(h1, pz, f.E[6], f.E[7]);
+			czv[k] = affine_finish(h2, pz, f.E[10], f.E[11]);
+			const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, czv[k]);
+			const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, czv[k]);
+			const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, czv[k]);
+			const int ix = __float2int_rd(__fdiv_rn(sx, sz)), iy = __float2int_rd(__fdiv_rn(sy, sz));
+			inb[k] = ix >= 0 && ix < f.W && iy >= 0 && iy < f.H;  // tsdf.cu:46
+			img[k] = inb[k] ? iy * f.W + ix : 0;
 		}
-		if (!any) continue;
-		const F sv = *reinterpret_cast<const F *>(p.sdf + v0);
-		I wv = *reinterpret_cast<const I *>(p.wt + v0);
-		F sn = sv;
-		float *sp = reinterpret_cast<float *>(&sn);
-		int *w = reinterpret_cast<int *>(&wv);
+		// phase 2: depth (metres, = depth/5000.f computed once per pixel by K0), all VEC loads at once
+		float dm[VEC];
+#pragma unroll
+		for (int k = 0; k < VEC; k++) dm[k] = __ldg(f.depth_m + img[k]);
+		// phase 3: tsdf.cu:48-52
+		float nd[VEC];
+		unsigned touched = 0, surface = 0;
 #pragma unroll
 		for (int k = 0; k < VEC; k++) {
-			if (ev[k].img < 0) continue;
-			const int wk = w[k];
-			sp[k] = sdf_update(sp[k], wk, ev[k].diff);
-			if (ev[k].diff < f.near_gate) {  // tsdf.cu:57-62
-				update_surface_voxel<LABELS>(p, f, v0 + k, wk, ev[k].img, err);
-				nS++;
+			const float diff = __fadd_rn(dm[k], -czv[k]);
+			// depth == 0 <=> dm == 0;  "diff <= -miu" rejects, NaN survives as in the reference
+			const bool t = inb[k] && dm[k] != 0.f && !(diff <= -g.miu);
+			// miu/miu == 1.0f exactly, so the clamped case needs no divide
+			nd[k] = (diff > g.miu) ? 1.0f : __fdiv_rn(diff, g.miu);
+			if (t) {
+				touched |= 1u << k;
+				if (nd[k] < f.near_gate) surface |= 1u << k;  // tsdf.cu:57
 			}
-			w[k] = wk + 1;  // tsdf.cu:68
-			nU++;
 		}
+		if (!touched) continue;
+		if (surface) {
+			// colour running mean + histogram increment (tsdf.cu:57-62); gather first, then apply
+			if (VEC == 4) {
+				uint32_t *cptr = reinterpret_cast<uint32_t *>(p.color + v0 * 3);  // v0 % 4 == 0 -> 4-byte aligned
+				uint32_t cw[3] = {cptr[0], cptr[1], cptr[2]};
+				uint32_t hv[VEC] = {}, lab[VEC] = {};
+				uint32_t src[VEC] = {};
+#pragma unroll
+				for (int k = 0; k < VEC; k++)
+					if ((surface >> k) & 1u) {
+						const uint8_t *sp3 = f.rgb + (size_t)img[k] * 3;
+						src[k] = (uint32_t)__ldg(sp3) | ((uint32_t)__ldg(sp3 + 1) << 8) | ((uint32_t)__ldg(sp3 + 2) << 16);
+						if (LABELS) {
+							lab[k] = __ldg(f.mask + img[k]);
+							if ((int)lab[k] < p.bins) hv[k] = p.hist[(v0 + k) * (size_t)p.bins + lab[k]];
+						}
+					}
+				uint8_t *cb = reinterpret_cast<uint8_t *>(cw);
+#pragma unroll
+				for (int k = 0; k < VEC; k++)
+					if ((surface >> k) & 1u) {
+						const int wk = w[k];
+#pragma unroll
+						for (int c = 0; c < 3; c++)
+							cb[k * 3 + c] = (uint8_t)(((int)cb[k * 3 + c] * wk + (int)((src[k] >> (8 * c)) & 0xffu)) / (wk + 1));
+						if (LABELS) {
+							if ((int)lab[k] < p.bins) p.hist[(v0 + k) * (size_t)p.bins + lab[k]] = hv[k] + 1u;
+							else atomicOr(err, 1u);
+						}
+						nS++;
+					}
+				cptr[0] = cw[0]; cptr[1] = cw[1]; cptr[2] = cw[2];
+			} else {
+#pragma unroll
+				for (int k = 0; k < VEC; k++)
+					if ((surface >> k) & 1u) {
+						update_surface_voxel<LABELS>(p, f, v0 + k, w[k], img[k], err);
+						nS++;
+					}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < VEC; k++)
+			if ((touched >> k) & 1u) {
+				sp[k] = sdf_update(sp[k], w[k], nd[k]);  // tsdf.cu:56
+				w[k] += 1;                                // tsdf.cu:68
+				nU++;
+			}
 		*reinterpret_cast<I *>(p.wt + v0) = wv;
 		if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 	}
+	}  // batch loop
 
-	// fold U / S: warp shuffle -> shared -> one spread atomic pair per block
+	// fold U / S: warp shuffle, then one spread atomic pair per warp (no block barrier: warps with
+	// little work must not hold their slot waiting for the busiest warp of the block)
 	nU = __reduce_add_sync(0xffffffffu, nU);
 	nS = __reduce_add_sync(0xffffffffu, nS);
-	__shared__ unsigned sU[8], sS[8];
-	if (lane == 0) { sU[warp] = nU; sS[warp] = nS; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned tu = 0, ts = 0;
-#pragma unroll
-		for (int i = 0; i < 8; i++) { tu += sU[i]; ts += sS[i]; }
-		if (tu | ts) {
-			const int slot = blockIdx.x % kStatSlots;
-			atomicAdd(stats + slot, (unsigned long long)tu);
-			atomicAdd(stats + kStatSlots + slot, (unsigned long long)ts);
-		}
+	if (lane == 0 && (nU | nS)) {
+		const int slot = (int)((blockIdx.x * 8 + warp) % kStatSlots);
+		atomicAdd(stats + slot, (unsigned long long)nU);
+		if (nS) atomicAdd(stats + kStatSlots + slot, (unsigned long long)nS);
 	}
 }
 

@@ -103,6 +103,8 @@ struct sfm_volume {
 	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
 	uint32_t *d_err = nullptr;
+	unsigned *d_work = nullptr;
+	int num_sms = 148;
 	uint8_t *d_palette = nullptr;
 	uint8_t *d_lut = nullptr;
 	// pinned staging (host), double buffered
@@ -246,10 +248,23 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	return f;
 }
 
+template <int VEC, bool LABELS, bool CULL>
+void launch_integrate2(sfm_volume *v, const FrameView &f, long long nbatches) {
+	// persistent grid: one resident wave (occupancy x SM count), never more blocks than batches need
+	static int per_sm = 0;
+	if (!per_sm) {
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrate_kernel<VEC, LABELS, CULL>, 256, 0) != cudaSuccess || per_sm < 1)
+			per_sm = 4;
+	}
+	const long long want = (nbatches + 7) / 8;
+	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));
+	integrate_kernel<VEC, LABELS, CULL><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err, v->d_work);
+}
+
 template <int VEC, bool LABELS>
-void launch_integrate(sfm_volume *v, const FrameView &f, bool cull, int blocks) {
-	if (cull) integrate_kernel<VEC, LABELS, true><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err);
-	else integrate_kernel<VEC, LABELS, false><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err);
+void launch_integrate(sfm_volume *v, const FrameView &f, bool cull, long long nbatches) {
+	if (cull) launch_integrate2<VEC, LABELS, true>(v, f, nbatches);
+	else launch_integrate2<VEC, LABELS, false>(v, f, nbatches);
 }
 
 // K0 + K1 on device-resident frame images
@@ -259,13 +274,13 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	const int prep_warps = v->TW * v->TH;
 	const int prep_blocks = (prep_warps * 32 + 255) / 256;
 	prep_frame_kernel<<<prep_blocks, 256, 0, v->stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
-		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err);
+		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err, v->d_work);
 	LAUNCH_CHECK(v);
 	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	const int cpw = vec4 ? 4 : 1;
 	const long long nbricks = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw) * ((v->g.nz + 31) / 32);
-	const int blocks = (int)((nbricks + 255) / 256);  // 8 warps x 32 bricks per block
+	const long long blocks = (nbricks + 31) / 32;  // number of 32-brick batches
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
 	if (vec4) {
@@ -590,6 +605,9 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
+	CU_OR_DESTROY(cudaMalloc(&v->d_work, 4));
+	CU_OR_DESTROY(cudaMemset(v->d_work, 0, 4));
+	v->num_sms = prop.multiProcessorCount;
 	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 4));
 	CU_OR_DESTROY(cudaMalloc(&v->d_palette, 256 * 3));
 	CU_OR_DESTROY(cudaMalloc(&v->d_lut, 256));
@@ -621,7 +639,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->stream) cudaStreamSynchronize(v->stream);
 	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist);
 	cudaFree(v->d_depth); cudaFree(v->d_rgb); cudaFree(v->d_mask); cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
-	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
+	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_fold);
 	for (int i = 0; i < 2; i++) {
