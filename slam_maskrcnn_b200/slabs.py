@@ -1,0 +1,108 @@
+"""z-slab sharding of one volume over the GPUs of a box: one process per GPU (torch.distributed).
+
+The reference is single-GPU; this is the scale-out of its path.  Integration
+is per-voxel independent (tsdf.cu:55-68 touches only its own voxel), so rank r simply owns the
+global z planes [z0, z0+nz) and integrates every frame into them; the only exchange is the frame
+itself, which rank `src` owns and broadcasts (ncclBroadcast over NVLink; gloo in the CPU tests).
+Voxel positions are computed from GLOBAL z indices (fma(z_global, voxel.z, start.z)), so a slab
+holds bit-identical values to the same planes of a single-GPU volume.
+
+Ray-casting a sharded volume composites per-ray first-hit keys with a MIN all-reduce
+(`composite_keys`): key = float_bits(t_hit) << 32 | label; t > 0 so the bit pattern orders like t.
+"""
+import numpy as np
+
+FRAME_W, FRAME_H = 640, 480
+
+
+def slab_range(rank, world, dz, align=4):
+    """Global z planes [z0, z0+nz) owned by `rank`: as even as possible, boundaries on multiples of
+    `align` (the 128-bit plane path needs nz % 4 == 0), the last rank takes the remainder."""
+    assert 0 <= rank < world and dz >= world
+    per = (dz // world) // align * align
+    if per == 0:
+        per, align = dz // world, 1
+    z0 = rank * per
+    nz = per if rank < world - 1 else dz - z0
+    return z0, nz
+
+
+def frame_nbytes(width=FRAME_W, height=FRAME_H):
+    return width * height * 6 + 64
+
+
+def pack_frame(depth, color, mask, extrinsic2init, out=None):
+    """[depth u16 | colour u8x3 | mask u8 | extrinsic2init f32x16] as one byte buffer (one broadcast)."""
+    h, w = depth.shape
+    n = w * h
+    buf = np.empty(frame_nbytes(w, h), np.uint8) if out is None else out
+    buf[:2 * n] = np.ascontiguousarray(depth, np.uint16).reshape(-1).view(np.uint8)
+    buf[2 * n:5 * n] = np.ascontiguousarray(color, np.uint8).reshape(-1)
+    buf[5 * n:6 * n] = np.ascontiguousarray(mask, np.uint8).reshape(-1)
+    buf[6 * n:] = np.ascontiguousarray(extrinsic2init, np.float32).reshape(-1).view(np.uint8)
+    return buf
+
+
+def unpack_frame(buf, width=FRAME_W, height=FRAME_H):
+    n = width * height
+    depth = buf[:2 * n].view(np.uint16).reshape(height, width)
+    color = buf[2 * n:5 * n].reshape(height, width, 3)
+    mask = buf[5 * n:6 * n].reshape(height, width)
+    pose = buf[6 * n:6 * n + 64].view(np.float32).reshape(4, 4)
+    return depth, color, mask, pose
+
+
+def frame_offsets(width=FRAME_W, height=FRAME_H):
+    n = width * height
+    return 0, 2 * n, 5 * n, 6 * n
+
+
+def composite_keys(keys, group=None):
+    """In-place MIN all-reduce of per-ray keys (int64 view of the u64 keys; all valid keys are < 2^63
+    because t > 0, and the 'no hit' key is mapped to INT64_MAX before the reduction)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return keys
+
+
+NO_HIT = np.int64(np.iinfo(np.int64).max)
+
+
+def keys_to_int64(keys_u64):
+    """u64 device keys -> int64 with UINT64_MAX (no hit) mapped to INT64_MAX so MIN works on signed ints."""
+    import torch
+    k = keys_u64.view(torch.int64)
+    return torch.where(k < 0, torch.full_like(k, int(NO_HIT)), k)
+
+
+class SlabVolume:
+    """This rank's slab of a volume sharded over `world` ranks."""
+
+    def __init__(self, dims, bins, rank, world, device=0, width=FRAME_W, height=FRAME_H, **kw):
+        from .tsdf import Volume
+        self.rank, self.world = rank, world
+        self.z0, self.nz = slab_range(rank, world, dims[2])
+        self.vol = Volume(dims=dims, bins=bins, width=width, height=height, device=device, slab=(self.z0, self.nz), **kw)
+        self.width, self.height = width, height
+
+    def set_bounds(self, *a, **k):
+        self.vol.set_bounds(*a, **k)
+
+    def broadcast_frame(self, packed_dev, src=0, group=None):
+        """`packed_dev`: CUDA uint8 tensor of frame_nbytes(); valid on `src`, overwritten elsewhere
+        (ncclBroadcast on the current stream).  Poses are not taken from the buffer: every rank reads
+        the (tiny) groundtruth.txt itself, so no device->host read-back is needed per frame."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.broadcast(packed_dev, src=src, group=group)
+        return packed_dev
+
+    def integrate_packed(self, packed_dev, extrinsic2init):
+        """Integrate a packed frame that is resident in this rank's HBM into this rank's slab."""
+        o_d, o_c, o_m, _ = frame_offsets(self.width, self.height)
+        p = packed_dev.data_ptr()
+        self.vol.integrate_dev(p + o_d, p + o_c, p + o_m, extrinsic2init)
+
+    def close(self):
+        self.vol.close()

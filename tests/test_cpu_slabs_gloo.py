@@ -1,0 +1,100 @@
+"""Host-side logic of the multi-GPU path on CPU: slab partition, frame packing, and the two
+collectives (frame broadcast, MIN composite of per-ray keys) over gloo with world_size 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_partition_covers_the_volume():
+    from slam_maskrcnn_b200.slabs import slab_range
+    for dz in (128, 512, 1024, 100, 37):
+        for world in (1, 2, 4, 8):
+            if dz < world:
+                continue
+            z = 0
+            for r in range(world):
+                z0, nz = slab_range(r, world, dz)
+                assert z0 == z and nz > 0
+                if r < world - 1 and dz // world >= 4:
+                    assert nz % 4 == 0
+                z += nz
+            assert z == dz
+
+
+def test_frame_pack_roundtrip():
+    from slam_maskrcnn_b200 import synth
+    from slam_maskrcnn_b200.slabs import pack_frame, unpack_frame, frame_nbytes
+    fr = synth.SynthScene(3).frame(2)
+    buf = pack_frame(fr["depth"], fr["color"], fr["mask"], fr["extrinsic"])
+    assert buf.nbytes == frame_nbytes() == 640 * 480 * 6 + 64
+    d, c, m, p = unpack_frame(buf)
+    assert (d == fr["depth"]).all() and (c == fr["color"]).all() and (m == fr["mask"]).all() and (p == fr["extrinsic"]).all()
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from slam_maskrcnn_b200 import synth
+    from slam_maskrcnn_b200.slabs import pack_frame, unpack_frame, composite_keys, slab_range, NO_HIT
+    from tests.common import Scenario
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # (1) frame broadcast: rank 0 owns the frame
+        sc = Scenario(dims=(32, 32, 32), bins=8, frames=2)
+        fr = sc.frames[1]
+        buf = torch.from_numpy(pack_frame(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"]) if rank == 0
+                               else np.zeros(sc.W * sc.H * 6 + 64, np.uint8))
+        dist.broadcast(buf, src=0)
+        d, c, m, p = unpack_frame(buf.numpy(), sc.W, sc.H)
+        ok_bcast = bool((d == fr["depth"]).all() and (c == fr["color"]).all() and (m == fr["gt"]).all() and (p == fr["extrinsic"]).all())
+        # (2) slab-sharded integration == whole-volume integration, plane by plane (CPU restatement per slab)
+        z0, nz = slab_range(rank, world, sc.dims[2])
+        whole = sc.make_cpu_volume()
+        mine = sc.make_cpu_volume()
+        for f in sc.frames:
+            whole.integrate(sc.K, f["depth"], f["color"], f["gt"], f["extrinsic"], sc.W, sc.H)
+            mine.integrate(sc.K, f["depth"], f["color"], f["gt"], f["extrinsic"], sc.W, sc.H, z_range=(z0, z0 + nz))
+        w, s = whole.planes(), mine.planes()
+        ok_slab = all((w[k][:, :, z0:z0 + nz] == s[k][:, :, z0:z0 + nz]).all() for k in ("weight", "color", "hist")) and \
+            (w["sdf"][:, :, z0:z0 + nz].view(np.uint32) == s["sdf"][:, :, z0:z0 + nz].view(np.uint32)).all()
+        untouched_elsewhere = (np.delete(s["weight"], np.s_[z0:z0 + nz], axis=2) == 0).all()
+        # (3) min-composite of per-ray keys: each rank "hits" a different subset
+        rng = np.random.default_rng(7)
+        t = rng.uniform(0.5, 6.0, (world, 64)).astype(np.float32)
+        lab = rng.integers(1, 8, (world, 64)).astype(np.int64)
+        hit = rng.random((world, 64)) < 0.6
+        keys_all = np.where(hit, (t.view(np.uint32).astype(np.int64) << 32) | lab, NO_HIT)
+        mine_k = torch.from_numpy(keys_all[rank].copy())
+        composite_keys(mine_k)
+        ok_comp = bool((mine_k.numpy() == keys_all.min(0)).all())
+        # the winner is the smallest t among the hitting ranks
+        tt = np.where(hit, t, np.inf)
+        win = tt.argmin(0)
+        any_hit = hit.any(0)
+        got_t = (mine_k.numpy() >> 32).astype(np.uint32).view(np.float32)
+        ok_order = bool((got_t[any_hit] == t[win, np.arange(64)][any_hit]).all())
+        q.put((rank, ok_bcast, ok_slab, bool(untouched_elsewhere), ok_comp, ok_order))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_broadcast_slabs_and_composite():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert all(r[1:]), f"rank {r[0]}: (bcast, slab, untouched, composite, order) = {r[1:]}"
