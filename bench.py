@@ -309,7 +309,8 @@ def run_ours(args):
         vol.integrate_dev(p, p + npx * 2, p + npx * 5, poses[j])
 
     def step_e2e(i):
-        """One step through the host-buffer C-ABI call; U/S counters read back."""
+        """One step through the host-buffer C-ABI call: H2D of this step's frame, K0 + K1, and the
+        read-back of the U/S counters -- enqueued for this step, consumed for the previous one."""
         j = i % n_pool
         if world > 1:
             buf = bcast_buf[i & 1]
@@ -321,7 +322,13 @@ def run_ours(args):
         else:
             b = packed_host[j].numpy()
             vol.integrate_raw(b[:npx * 2].view(np.uint16), b[npx * 2:npx * 5], b[npx * 5:npx * 6], poses[j])
-        return vol.frame_stats()
+        ticket = vol.stats_begin()
+        prev = e2e_state.get("ticket")
+        e2e_state["ticket"] = ticket
+        if prev is not None:
+            e2e_state["totals"] = vol.stats_end(prev)
+
+    e2e_state = {}
 
     def barrier():
         if world > 1:
@@ -374,6 +381,7 @@ def run_ours(args):
     ev0.record()
     for i in range(K_steps):
         step_e2e(W_steps + i)
+    e2e_state["totals"] = vol.stats_end(e2e_state["ticket"])  # the last step's result
     ev1.record()
     barrier()
     t_e2e_wall = time.perf_counter() - t0
@@ -460,8 +468,8 @@ def run_ours(args):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "voxel-updates/s", "h2d_bytes_per_step": FRAME_BYTES,
                     "d2h_bytes_per_step": 4096, "ms_per_step": t_e2e_ms / K_steps, "wall_ms_per_step": 1e3 * t_e2e_wall / K_steps,
-                    "api": "sfm_integrate_raw(host pinned depth,colour,mask, pose) + sfm_frame_stats" if world == 1 else
-                           "pinned host frame -> H2D on rank 0 -> ncclBroadcast -> sfm_integrate_dev + sfm_frame_stats"},
+                    "api": "sfm_integrate_raw(host pinned depth,colour,mask, pose) + sfm_stats_begin/_end (U,S of step i-1 read while step i runs)" if world == 1 else
+                           "pinned host frame -> H2D on rank 0 -> ncclBroadcast -> sfm_integrate_dev + sfm_stats_begin/_end"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "fused_merge_path": fused,

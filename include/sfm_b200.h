@@ -193,6 +193,12 @@ int sfm_integrate_times(sfm_volume *v, float *ms, int n);
  * algorithmic-bytes formula 16*U + 14*S. */
 int sfm_frame_stats(sfm_volume *v, uint64_t *U, uint64_t *S);
 
+/* Pipelined read-back of the same counters: _begin enqueues the D2H copy after the work submitted
+ * so far and returns a ticket (ring of 4); _end waits for that ticket only and returns the
+ * CUMULATIVE totals at that point, so step i-1's result can be read while step i runs. */
+int sfm_stats_begin(sfm_volume *v, uint64_t *ticket);
+int sfm_stats_end(sfm_volume *v, uint64_t ticket, uint64_t *U_total, uint64_t *S_total);
+
 /* Host-side helpers of the reference's driver (the "next" rows). */
 /* mean_depth (utils.cu:77-91). */
 float sfm_mean_depth(const uint16_t *depth, int n);

@@ -88,6 +88,8 @@ SYMBOLS = {
     "sfm_last_integrate_ms": (_i, [_vp, C.POINTER(_f)]),
     "sfm_integrate_times": (_i, [_vp, _vp, _i]),
     "sfm_frame_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "sfm_stats_begin": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "sfm_stats_end": (_i, [_vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_mean_depth": (_f, [_vp, _i]),
     "sfm_parse_extrinsic": (None, [_vp, _vp]),
 }

@@ -96,9 +96,20 @@ struct sfm_volume {
 	int bins = 0, W = 0, H = 0, TW = 0, TH = 0;
 	size_t nvox = 0;
 	Planes planes{};
-	// frame staging (device)
-	uint16_t *d_depth = nullptr;
+	// frame staging (device): double buffered, filled on a dedicated copy stream so that the H2D
+	// copy of frame i+1 overlaps the kernels of frame i
+	uint16_t *d_depth = nullptr;                 // = current buffer
 	uint8_t *d_rgb = nullptr, *d_mask = nullptr;
+	uint8_t *d_frame[2] = {nullptr, nullptr};    // [depth | rgb | mask]
+	cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+	int frame_cur = 0;
+	bool frame_open = false;
+	cudaStream_t copy_stream = nullptr;
+	// pipelined read-back of the U/S counters
+	static constexpr int kStatRing = 4;
+	unsigned long long *h_stat_ring = nullptr;   // pinned, kStatRing x 2*kStatSlots
+	cudaEvent_t ev_stat[kStatRing] = {};
+	uint64_t stat_tickets = 0;
 	uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;
 	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
@@ -195,26 +206,46 @@ bool is_device_or_pinned(const void *p) {
 	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// Upload one frame's images to the device staging buffers.  Pinned / device sources are copied
-// directly and asynchronously; pageable sources go through a double-buffered pinned bounce buffer.
+// Upload one frame's images into the next device frame buffer on the copy stream.  Pinned / device
+// sources are copied directly; pageable sources go through a double-buffered pinned bounce buffer.
+// The compute stream is made to wait for the upload; release_frame() marks the buffer reusable.
 int upload_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask) {
 	const size_t npx = (size_t)v->W * v->H;
 	const size_t bd = npx * 2, bc = npx * 3, bm = npx;
+	const int b = v->frame_cur ^ 1;
+	v->frame_cur = b;
+	uint8_t *base = v->d_frame[b];
+	v->d_depth = (uint16_t *)base;
+	v->d_rgb = base + bd;
+	v->d_mask = base + bd + bc;
+	CU(cudaStreamWaitEvent(v->copy_stream, v->ev_consumed[b], 0));  // kernels that read this buffer are done
 	const bool direct = (!depth || is_device_or_pinned(depth)) && (!color || is_device_or_pinned(color)) &&
 		(!mask || is_device_or_pinned(mask));
 	if (direct) {
-		if (depth) CU(cudaMemcpyAsync(v->d_depth, depth, bd, cudaMemcpyDefault, v->stream));
-		if (color) CU(cudaMemcpyAsync(v->d_rgb, color, bc, cudaMemcpyDefault, v->stream));
-		if (mask) CU(cudaMemcpyAsync(v->d_mask, mask, bm, cudaMemcpyDefault, v->stream));
-		return SFM_OK;
+		if (depth) CU(cudaMemcpyAsync(v->d_depth, depth, bd, cudaMemcpyDefault, v->copy_stream));
+		if (color) CU(cudaMemcpyAsync(v->d_rgb, color, bc, cudaMemcpyDefault, v->copy_stream));
+		if (mask) CU(cudaMemcpyAsync(v->d_mask, mask, bm, cudaMemcpyDefault, v->copy_stream));
+	} else {
+		PinnedFrame &pf = v->pin[v->pin_next];
+		v->pin_next ^= 1;
+		CU(cudaEventSynchronize(pf.free_ev));
+		if (depth) { memcpy(pf.buf, depth, bd); CU(cudaMemcpyAsync(v->d_depth, pf.buf, bd, cudaMemcpyHostToDevice, v->copy_stream)); }
+		if (color) { memcpy(pf.buf + bd, color, bc); CU(cudaMemcpyAsync(v->d_rgb, pf.buf + bd, bc, cudaMemcpyHostToDevice, v->copy_stream)); }
+		if (mask) { memcpy(pf.buf + bd + bc, mask, bm); CU(cudaMemcpyAsync(v->d_mask, pf.buf + bd + bc, bm, cudaMemcpyHostToDevice, v->copy_stream)); }
+		CU(cudaEventRecord(pf.free_ev, v->copy_stream));
 	}
-	PinnedFrame &pf = v->pin[v->pin_next];
-	v->pin_next ^= 1;
-	CU(cudaEventSynchronize(pf.free_ev));
-	if (depth) { memcpy(pf.buf, depth, bd); CU(cudaMemcpyAsync(v->d_depth, pf.buf, bd, cudaMemcpyHostToDevice, v->stream)); }
-	if (color) { memcpy(pf.buf + bd, color, bc); CU(cudaMemcpyAsync(v->d_rgb, pf.buf + bd, bc, cudaMemcpyHostToDevice, v->stream)); }
-	if (mask) { memcpy(pf.buf + bd + bc, mask, bm); CU(cudaMemcpyAsync(v->d_mask, pf.buf + bd + bc, bm, cudaMemcpyHostToDevice, v->stream)); }
-	CU(cudaEventRecord(pf.free_ev, v->stream));
+	CU(cudaEventRecord(v->ev_uploaded[b], v->copy_stream));
+	CU(cudaStreamWaitEvent(v->stream, v->ev_uploaded[b], 0));
+	v->frame_open = true;
+	return SFM_OK;
+}
+
+// The kernels enqueued so far were the last readers of the current frame buffer.
+int release_frame(sfm_volume *v) {
+	if (v->frame_open) {
+		CU(cudaEventRecord(v->ev_consumed[v->frame_cur], v->stream));
+		v->frame_open = false;
+	}
 	return SFM_OK;
 }
 
@@ -595,10 +626,18 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	if (v->bins > 0) CU_OR_DESTROY(cudaMalloc(&v->planes.hist, v->nvox * 4 * (size_t)v->bins));
 	v->planes.bins = v->bins;
 	const size_t npx = (size_t)v->W * v->H;
-	CU_OR_DESTROY(cudaMalloc(&v->d_depth, npx * 2));
-	CU_OR_DESTROY(cudaMalloc(&v->d_rgb, npx * 3));
-	CU_OR_DESTROY(cudaMalloc(&v->d_mask, npx));
-	CU_OR_DESTROY(cudaMemset(v->d_mask, 0, npx));
+	CU_OR_DESTROY(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CU_OR_DESTROY(cudaMalloc(&v->d_frame[i], npx * 6));
+		CU_OR_DESTROY(cudaMemset(v->d_frame[i], 0, npx * 6));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_uploaded[i], cudaEventDisableTiming));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_consumed[i], cudaEventDisableTiming));
+	}
+	v->d_depth = (uint16_t *)v->d_frame[0];
+	v->d_rgb = v->d_frame[0] + npx * 2;
+	v->d_mask = v->d_frame[0] + npx * 5;
+	CU_OR_DESTROY(cudaMallocHost(&v->h_stat_ring, (size_t)sfm_volume::kStatRing * 2 * kStatSlots * 8));
+	for (int i = 0; i < sfm_volume::kStatRing; i++) CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_stat[i], cudaEventDisableTiming));
 	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, (size_t)v->TW * v->TH * 2));
 	CU_OR_DESTROY(cudaMalloc(&v->d_tilemin, (size_t)v->TW * v->TH * 2));
 	CU_OR_DESTROY(cudaMalloc(&v->d_depth_m, npx * 4));
@@ -638,7 +677,16 @@ void sfm_destroy(sfm_volume *v) {
 	cudaSetDevice(v->desc.device);
 	if (v->stream) cudaStreamSynchronize(v->stream);
 	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist);
-	cudaFree(v->d_depth); cudaFree(v->d_rgb); cudaFree(v->d_mask); cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
+	if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
+	for (int i = 0; i < 2; i++) {
+		cudaFree(v->d_frame[i]);
+		if (v->ev_uploaded[i]) cudaEventDestroy(v->ev_uploaded[i]);
+		if (v->ev_consumed[i]) cudaEventDestroy(v->ev_consumed[i]);
+	}
+	if (v->h_stat_ring) cudaFreeHost(v->h_stat_ring);
+	for (int i = 0; i < sfm_volume::kStatRing; i++) if (v->ev_stat[i]) cudaEventDestroy(v->ev_stat[i]);
+	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+	cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
 	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_fold);
@@ -719,7 +767,9 @@ int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
 	int rc = upload_frame(v, depth, color, v->bins > 0 ? mask : nullptr);
 	if (rc) return rc;
-	return integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+	rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+	if (rc) return rc;
+	return release_frame(v);
 }
 
 int sfm_overlap_tables(sfm_volume *v, const float *E16, const uint8_t *mask, double *A, uint32_t *C) {
@@ -735,6 +785,8 @@ int sfm_overlap_tables(sfm_volume *v, const float *E16, const uint8_t *mask, dou
 	rc = upload_frame(v, nullptr, nullptr, mask);
 	if (rc) return rc;
 	rc = run_fold(v, E16, v->d_mask);
+	if (rc) return rc;
+	rc = release_frame(v);
 	if (rc) return rc;
 	combine_tables(v, mx + 1, A, C);
 	return SFM_OK;
@@ -797,8 +849,8 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 			LAUNCH_CHECK(v);
 			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
 			if (rc) return rc;
+			// (the LUT copy above is from pageable memory: the runtime stages it before returning)
 			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // overlaps the kernel
-			CU(cudaStreamSynchronize(v->stream));  // lut (stack) must outlive the async copy
 		} else {
 			v->num_objs = mx + 1;  // tsdf.cu:464-467
 			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
@@ -810,7 +862,7 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 		rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
 		if (rc) return rc;
 	}
-	return SFM_OK;
+	return release_frame(v);
 }
 
 int sfm_parse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
@@ -1015,6 +1067,31 @@ int sfm_frame_stats(sfm_volume *v, uint64_t *U, uint64_t *S) {
 	*S = s - v->stat_S_seen;
 	v->stat_U_seen = u;
 	v->stat_S_seen = s;
+	return SFM_OK;
+}
+
+/* Pipelined form: _begin enqueues the read-back of the counters after the work submitted so far and
+ * returns a ticket; _end waits for that ticket only and returns the CUMULATIVE totals at that point,
+ * so a caller can read step i-1's result while step i is already running. */
+int sfm_stats_begin(sfm_volume *v, uint64_t *ticket) {
+	if (!v || !ticket) return fail(SFM_ERR_INVALID, "null argument");
+	const int slot = (int)(v->stat_tickets % sfm_volume::kStatRing);
+	CU(cudaMemcpyAsync(v->h_stat_ring + (size_t)slot * 2 * kStatSlots, v->d_stats, 2 * kStatSlots * 8, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaEventRecord(v->ev_stat[slot], v->stream));
+	*ticket = v->stat_tickets++;
+	return SFM_OK;
+}
+
+int sfm_stats_end(sfm_volume *v, uint64_t ticket, uint64_t *U_total, uint64_t *S_total) {
+	if (!v || !U_total || !S_total) return fail(SFM_ERR_INVALID, "null argument");
+	if (ticket >= v->stat_tickets || ticket + sfm_volume::kStatRing < v->stat_tickets) return fail(SFM_ERR_INVALID, "stale or unknown stats ticket");
+	const int slot = (int)(ticket % sfm_volume::kStatRing);
+	CU(cudaEventSynchronize(v->ev_stat[slot]));
+	const unsigned long long *h = v->h_stat_ring + (size_t)slot * 2 * kStatSlots;
+	uint64_t u = 0, s2 = 0;
+	for (int i = 0; i < kStatSlots; i++) { u += h[i]; s2 += h[kStatSlots + i]; }
+	*U_total = u;
+	*S_total = s2;
 	return SFM_OK;
 }
 

@@ -238,6 +238,16 @@ class Volume:
         check(self.lib.sfm_integrate_times(self._h, _ptr(ms), n))
         return ms
 
+    def stats_begin(self):
+        t = C.c_uint64()
+        check(self.lib.sfm_stats_begin(self._h, C.byref(t)))
+        return int(t.value)
+
+    def stats_end(self, ticket):
+        u, s = C.c_uint64(), C.c_uint64()
+        check(self.lib.sfm_stats_end(self._h, C.c_uint64(ticket), C.byref(u), C.byref(s)))
+        return int(u.value), int(s.value)
+
     def frame_stats(self):
         u, s = C.c_uint64(), C.c_uint64()
         check(self.lib.sfm_frame_stats(self._h, C.byref(u), C.byref(s)))
