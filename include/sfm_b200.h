@@ -199,6 +199,10 @@ int sfm_frame_stats(sfm_volume *v, uint64_t *U, uint64_t *S);
 int sfm_stats_begin(sfm_volume *v, uint64_t *ticket);
 int sfm_stats_end(sfm_volume *v, uint64_t ticket, uint64_t *U_total, uint64_t *S_total);
 
+/* Test hook: number of operands (out of blocks*256*per_thread pseudo-random ones) for which the
+ * invariant-divisor division used by the ray-marcher differs from the IEEE divide a/b.  Must be 0. */
+int sfm_debug_divcheck(float b, unsigned seed, int blocks, int per_thread, float amax, uint64_t *mismatches);
+
 /* Host-side helpers of the reference's driver (the "next" rows). */
 /* mean_depth (utils.cu:77-91). */
 float sfm_mean_depth(const uint16_t *depth, int n);

@@ -90,6 +90,7 @@ SYMBOLS = {
     "sfm_frame_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_stats_begin": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "sfm_stats_end": (_i, [_vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "sfm_debug_divcheck": (_i, [_f, C.c_uint, _i, _i, _f, C.POINTER(C.c_uint64)]),
     "sfm_mean_depth": (_f, [_vp, _i]),
     "sfm_parse_extrinsic": (None, [_vp, _vp]),
 }

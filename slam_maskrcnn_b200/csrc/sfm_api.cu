@@ -129,6 +129,7 @@ struct sfm_volume {
 	uint8_t *d_flags = nullptr;
 	uint8_t *d_bgr = nullptr, *d_label = nullptr;
 	unsigned long long *d_keys = nullptr;
+	float4 *d_hits = nullptr;
 	size_t ray_px = 0;      // capacity of the per-pixel buffers
 	size_t probs_px = 0;    // capacity of probs/box
 	// merge scratch
@@ -331,9 +332,10 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 
 int ensure_ray_buffers(sfm_volume *v, size_t px, bool want_probs) {
 	if (px > v->ray_px) {
-		cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr); cudaFree(v->d_label); cudaFree(v->d_keys);
-		v->d_t = nullptr; v->d_flags = nullptr; v->d_bgr = nullptr; v->d_label = nullptr; v->d_keys = nullptr;
+		cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr); cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits);
+		v->d_t = nullptr; v->d_flags = nullptr; v->d_bgr = nullptr; v->d_label = nullptr; v->d_keys = nullptr; v->d_hits = nullptr;
 		v->ray_px = 0;
+		CU(cudaMalloc(&v->d_hits, px * sizeof(float4)));
 		CU(cudaMalloc(&v->d_t, px * 4));
 		CU(cudaMalloc(&v->d_flags, px));
 		CU(cudaMalloc(&v->d_bgr, px * 3));
@@ -433,15 +435,20 @@ int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	tb.FirstPix = (unsigned *)(v->d_fold + fl.oFirst);
 	const RayVol V = make_ray_vol(v);
 	const RayCam cam = make_backproj_cam(v, E16);
-	const int blocks = ray_blocks(v->W, v->H);
+	const int npix = v->W * v->H;
+	int rc = ensure_ray_buffers(v, (size_t)npix, false);
+	if (rc) return rc;
+	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr);
+	LAUNCH_CHECK(v);
+	const int blocks = (npix + 127) / 128;
 	const float n_obs = (float)v->n_obs, prior = v->desc.prior_err_rate, pres = v->desc.presence_thresh;
 	const int nb = (L + 31) / 32;
 	switch (nb) {
-	case 1: backproject_fold_kernel<1><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
-	case 2: backproject_fold_kernel<2><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
-	case 3: backproject_fold_kernel<3><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
-	case 4: backproject_fold_kernel<4><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
-	default: backproject_fold_kernel<8><<<blocks, 128, 0, v->stream>>>(V, cam, d_mask, n_obs, prior, pres, tb); break;
+	case 1: fold_kernel<1><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
+	case 2: fold_kernel<2><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
+	case 3: fold_kernel<3><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
+	case 4: fold_kernel<4><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
+	default: fold_kernel<8><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
 	}
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(v->h_fold, v->d_fold, fl.total, cudaMemcpyDeviceToHost, v->stream));
@@ -689,7 +696,7 @@ void sfm_destroy(sfm_volume *v) {
 	cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
 	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
-	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_fold);
+	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);
 	for (int i = 0; i < 2; i++) {
 		if (v->pin[i].buf) cudaFreeHost(v->pin[i].buf);
 		if (v->pin[i].free_ev) cudaEventDestroy(v->pin[i].free_ev);
@@ -715,6 +722,13 @@ int sfm_set_bounds(sfm_volume *v, const float *vol_start3, const float *vol_end3
 	v->g.ex = vol_end3[0]; v->g.ey = vol_end3[1]; v->g.ez = vol_end3[2];
 	v->g.vx = voxel3[0]; v->g.vy = voxel3[1]; v->g.vz = voxel3[2];
 	v->g.miu = miu;
+	v->g.fastdiv = 0;
+	for (int a = 0; a < 3; a++) {  // see div_by() in k_raymarch.cuh
+		uint32_t bits;
+		memcpy(&bits, &voxel3[a], 4);
+		const float av = fabsf(voxel3[a]);
+		if ((bits & 0x7fffffu) != 0x7fffffu && av > 1e-18f && av < 1e18f) v->g.fastdiv |= 1 << a;
+	}
 	v->init = true;
 	for (int i = 0; i < 16; i++) v->init_extr_inv[i] = (i % 5 == 0) ? 1.f : 0.f;
 	return reset_planes(v);
@@ -887,8 +901,10 @@ int sfm_backproject(sfm_volume *v, const float *E16, float *probs, uint8_t *box_
 	if (rc) return rc;
 	CU(cudaMemsetAsync(v->d_probs, 0, npx * v->bins * 4, v->stream));  // tsdf.cu:428-429
 	CU(cudaMemsetAsync(v->d_box, 0, npx * v->bins, v->stream));
-	backproject_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16),
-		v->desc.presence_thresh, v->d_probs, v->d_box, v->d_t, v->d_flags);
+	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16), v->d_hits, v->d_flags);
+	LAUNCH_CHECK(v);
+	probs_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->desc.presence_thresh,
+		v->d_probs, v->d_box, v->d_t, v->d_flags);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(probs, v->d_probs, npx * v->bins * 4, cudaMemcpyDeviceToHost, v->stream));  // tsdf.cu:457-458
 	CU(cudaMemcpyAsync(box_mask, v->d_box, npx * v->bins, cudaMemcpyDeviceToHost, v->stream));
@@ -904,7 +920,11 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	CU(cudaSetDevice(v->desc.device));
 	int rc = require_full_volume(v, "sfm_raycast_keys_dev");
 	if (rc) return rc;
-	raycast_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_palette,
+	rc = ensure_ray_buffers(v, (size_t)w * h, false);
+	if (rc) return rc;
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr);
+	LAUNCH_CHECK(v);
+	shade_kernel<<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
 		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
@@ -919,7 +939,9 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	const size_t npx = (size_t)w * h;
 	rc = ensure_ray_buffers(v, npx, false);
 	if (rc) return rc;
-	raycast_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_palette,
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags);
+	LAUNCH_CHECK(v);
+	shade_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
 		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));  // viewer.cu:167
@@ -1092,6 +1114,24 @@ int sfm_stats_end(sfm_volume *v, uint64_t ticket, uint64_t *U_total, uint64_t *S
 	for (int i = 0; i < kStatSlots; i++) { u += h[i]; s2 += h[kStatSlots + i]; }
 	*U_total = u;
 	*S_total = s2;
+	return SFM_OK;
+}
+
+/* test hook: mismatches between the invariant-divisor division used by the ray-marcher and the IEEE divide */
+int sfm_debug_divcheck(float b, unsigned seed, int blocks, int per_thread, float amax, uint64_t *mismatches) {
+	if (!mismatches) return fail(SFM_ERR_INVALID, "null argument");
+	unsigned long long *d = nullptr;
+	CU(cudaMalloc(&d, 8));
+	CU(cudaMemset(d, 0, 8));
+	uint32_t bits;
+	memcpy(&bits, &b, 4);
+	const bool ok = (bits & 0x7fffffu) != 0x7fffffu && fabsf(b) > 1e-18f && fabsf(b) < 1e18f;
+	divcheck_kernel<<<blocks, 256>>>(b, ok, seed, per_thread, amax, d);
+	unsigned long long h = 0;
+	cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(SFM_ERR_CUDA, cudaGetErrorString(e));
+	*mismatches = h;
 	return SFM_OK;
 }
 

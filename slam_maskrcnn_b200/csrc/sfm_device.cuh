@@ -21,6 +21,7 @@ struct VolGeom {
 	float ex, ey, ez;  // vol_end_
 	float vx, vy, vz;  // vol_res_
 	float miu;
+	int fastdiv;  // bit a set: dividing by voxel[a] may use the invariant-divisor sequence (k_raymarch.cuh)
 };
 
 struct Planes {

@@ -228,3 +228,18 @@ def test_raycast_close_to_cpu_oracle():
     assert both.mean() > 0.3
     np.testing.assert_allclose(t[both], ot[both], rtol=1e-3)
     v.close()
+
+
+def test_invariant_divisor_division_is_ieee_exact():
+    """div_by() (k_raymarch.cuh) must equal the IEEE divide bit for bit: 3 x 2^24 pseudo-random operands per divisor."""
+    import ctypes as C
+    from slam_maskrcnn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    divisors = [0.009473, 0.0189, 0.07673594, 0.061194, 1.0, 3.0, 1e-3, 0.3333333, float(np.float32(1.9999999)), 7.5e-5]
+    divisors += [float(x) for x in rng.uniform(1e-3, 0.2, 12).astype(np.float32)]
+    for b in divisors:
+        for amax in (8.0, 1e3):
+            bad = C.c_uint64(123)
+            _lib.check(lib.sfm_debug_divcheck(C.c_float(b), 17, 256, 256, C.c_float(amax), C.byref(bad)))
+            assert bad.value == 0, f"divisor {b}: {bad.value} mismatches"
