@@ -70,61 +70,42 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restr
 // ---------------------------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------------------------
-struct VoxelEval {
-	int img;     // pixel index, -1 => voxel rejected before the update
-	float diff;  // normalised, clamped SDF sample
-};
+// tsdf.cu:39-44: ix = floor(RN(sx/sz)), iy = floor(RN(sy/sz)).  Only the floors are needed, so the two
+// IEEE divides are replaced by one MUFU.RCP and two multiplies: q~ = sx*rcp(sz) is within
+// 2.4e-7*|q| of the correctly rounded quotient q (rcp.approx: 1 ulp, the product: 1/2 ulp, q itself:
+// 1/2 ulp), hence floor(q~) == floor(q) whenever q~ is farther than that from every integer.  The test
+// uses twice that distance; otherwise (about 1 voxel in 10^4, and for NaN/inf/huge values) the exact
+// divides decide.  Bit-identical to the reference by construction.
+// Rarely executed exact paths are kept out of line: with everything inlined the kernel is 43 KB of
+// SASS and the profile shows instruction-fetch stalls (the instruction cache holds 32 KB).
+__device__ __noinline__ float exact_div(float a, float b) { return __fdiv_rn(a, b); }
 
-// tsdf.cu:30-52 for one voxel whose z-invariant parts are hoisted.
-__device__ __forceinline__ VoxelEval eval_voxel(const FrameView &f, const VolGeom &g, float h0, float h1,
-	float h2, int zglobal)
-{
-	VoxelEval r;
-	r.img = -1;
-	r.diff = 0.f;
-	const float pz = __fmaf_rn((float)zglobal, g.vz, g.sz);
-	const float cx = affine_finish(h0, pz, f.E[2], f.E[3]);
-	const float cy = affine_finish(h1, pz, f.E[6], f.E[7]);
-	const float cz = affine_finish(h2, pz, f.E[10], f.E[11]);
-	float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
-	float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
-	const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
-	sx = __fdiv_rn(sx, sz);
-	sy = __fdiv_rn(sy, sz);
-	const int ix = __float2int_rd(sx), iy = __float2int_rd(sy);
-	if (ix < 0 || ix >= f.W || iy < 0 || iy >= f.H) return r;
-	const int img = iy * f.W + ix;
-	const float dm = __ldg(f.depth_m + img);  // = depth/5000.f, IEEE divide done once per pixel in K0
-	if (dm == 0.f) return r;                  // depth == 0  (depth >= 1 gives dm > 0)
-	float diff = __fadd_rn(dm, -cz);
-	if (diff <= -g.miu) return r;  // NaN survives, as in the reference
-	// tsdf.cu:51-52: clamp, then diff/miu.  miu/miu == 1.0f exactly, so the clamped case needs no divide.
-	r.diff = (diff > g.miu) ? 1.0f : __fdiv_rn(diff, g.miu);
-	r.img = img;
-	return r;
+// true when floor(q~) is guaranteed to equal floor(RN(s/sz)) for both coordinates (see pixel_floor)
+__device__ __forceinline__ bool pixel_floor_is_safe(float qx, float qy) {
+	return fabsf(__fadd_rn(qx, -rintf(qx))) > __fmaf_rn(fabsf(qx), 4.8e-7f, 1e-30f) &&
+		fabsf(__fadd_rn(qy, -rintf(qy))) > __fmaf_rn(fabsf(qy), 4.8e-7f, 1e-30f);
+}
+
+__device__ __forceinline__ void pixel_floor(float sx, float sy, float sz, int &ix, int &iy) {
+	float r;
+	asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(sz));
+	const float qx = __fmul_rn(sx, r), qy = __fmul_rn(sy, r);
+	const bool okx = fabsf(__fadd_rn(qx, -rintf(qx))) > __fmaf_rn(fabsf(qx), 4.8e-7f, 1e-30f);
+	const bool oky = fabsf(__fadd_rn(qy, -rintf(qy))) > __fmaf_rn(fabsf(qy), 4.8e-7f, 1e-30f);
+	if (okx && oky) {
+		ix = __float2int_rd(qx);
+		iy = __float2int_rd(qy);
+	} else {
+		ix = __float2int_rd(exact_div(sx, sz));
+		iy = __float2int_rd(exact_div(sy, sz));
+	}
 }
 
 // tsdf.cu:56  (sdf*w + diff)/(w+1)  -> FFMA, IEEE divide.  (1.0f*w + 1.0f)/(w+1) is exactly 1.0f
 // for 0 <= w < 2^24 (both the fma and the quotient are exact), so that case skips the divide.
 __device__ __forceinline__ float sdf_update(float s, int w, float diff) {
 	if (s == 1.0f && diff == 1.0f && (unsigned)w < (1u << 24)) return 1.0f;
-	return __fdiv_rn(__fmaf_rn(s, (float)w, diff), (float)(w + 1));
-}
-
-// colour running mean + histogram increment (tsdf.cu:57-62) for one near-surface voxel
-template <bool LABELS>
-__device__ __forceinline__ void update_surface_voxel(const Planes &p, const FrameView &f, size_t v, int w,
-	int img, uint32_t *err)
-{
-	const uint8_t *src = f.rgb + (size_t)img * 3;
-	uint8_t *dst = p.color + v * 3;
-#pragma unroll
-	for (int c = 0; c < 3; c++) dst[c] = (uint8_t)(((int)dst[c] * w + (int)__ldg(src + c)) / (w + 1));
-	if (LABELS) {
-		const unsigned label = __ldg(f.mask + img);
-		if ((int)label < p.bins) p.hist[v * (size_t)p.bins + label] += 1u;
-		else atomicOr(err, 1u);
-	}
+	return exact_div(__fmaf_rn(s, (float)w, diff), (float)(w + 1));
 }
 
 template <int VEC> struct VecT;
@@ -141,6 +122,46 @@ __device__ __forceinline__ bool same_bits(const float &a, const float &b) {
 
 enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
 
+constexpr int kQueue = 256;  // per-warp capacity of the deferred near-surface queue (>= 2 bricks of 128 voxels)
+
+// Colour running mean + histogram increment (tsdf.cu:57-62) for the queued near-surface voxels, one
+// voxel per lane: the label -> histogram-bin dependent loads of 32 voxels are in flight together.
+// Every voxel appears at most once per frame, so the read-modify-writes need no atomics; colour is
+// written with byte stores so neighbouring voxels' bytes are never touched.
+template <bool LABELS>
+__device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const FrameView &f, const uint4 *q, int count,
+	int lane, uint32_t *err)
+{
+	__syncwarp();
+	unsigned done = 0;
+	for (int base = 0; base < count; base += 32) {
+		const int i = base + lane;
+		if (i < count) {
+			const uint4 e = q[i];
+			const size_t v = (size_t)e.x | ((size_t)e.y << 32);
+			const int img = (int)e.z, w = (int)e.w;
+			const uint8_t *src = f.rgb + (size_t)img * 3;
+			uint8_t *dst = p.color + v * 3;
+			const int s0 = __ldg(src), s1 = __ldg(src + 1), s2 = __ldg(src + 2);
+			const int c0 = dst[0], c1 = dst[1], c2 = dst[2];
+			unsigned label = 0, hv = 0;
+			uint32_t *hp = nullptr;
+			if (LABELS) {
+				label = __ldg(f.mask + img);
+				if ((int)label < p.bins) { hp = p.hist + v * (size_t)p.bins + label; hv = *hp; }
+				else atomicOr(err, 1u);
+			}
+			dst[0] = (uint8_t)((c0 * w + s0) / (w + 1));
+			dst[1] = (uint8_t)((c1 * w + s1) / (w + 1));
+			dst[2] = (uint8_t)((c2 * w + s2) / (w + 1));
+			if (LABELS && hp) *hp = hv + 1u;
+			done++;
+		}
+	}
+	__syncwarp();
+	return done;
+}
+
 // Stage A: classify one brick (x, columns y0..ylast, local z zc0..zc1).
 __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, int x, int y0, int ylast,
 	int zc0, int zc1)
@@ -148,7 +169,7 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 	const float px = __fmaf_rn((float)x, g.vx, g.sx);
 	float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
 	float szmin = INFINITY, szmax = -INFINITY, czmin = INFINITY, czmax = -INFINITY, scale_c = 0.f;
-#pragma unroll
+#pragma unroll 1
 	for (int corner = 0; corner < 4; corner++) {
 		const float py = __fmaf_rn((float)((corner & 1) ? ylast : y0), g.vy, g.sy);
 		const float pz = __fmaf_rn((float)(g.z0 + ((corner & 2) ? zc1 : zc0)), g.vz, g.sz);
@@ -225,6 +246,9 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 	// warp that lands on culled space immediately moves on instead of idling in a resident block.
 	const long long nbatches = (nbricks + 31) >> 5;
 	unsigned nU = 0, nS = 0;
+	__shared__ uint4 queue_mem[8][kQueue];  // per-warp deferred near-surface voxels: {voxel lo, hi, pixel, weight}
+	uint4 *q = queue_mem[warp];
+	int qcount = 0;  // warp-uniform
 	for (;;) {
 	long long batch = 0;
 	if (lane == 0) batch = atomicAdd(work_counter, 1u);
@@ -236,8 +260,12 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 	int cls = kCull;
 	int bx = 0, by0 = 0, bzc = 0;
 	{
-		const long long b = warp_base + lane;
+		// bricks are dealt to the batches through a multiplicative permutation (g.brick_mul is coprime
+		// with nbricks): every batch samples the whole volume, so all batches carry about the same
+		// number of surviving bricks and no warp is left finishing a dense batch alone at the end
+		long long b = warp_base + lane;
 		if (b < nbricks) {
+			b = (long long)(((unsigned long long)b * (unsigned long long)g.brick_mul) % (unsigned long long)nbricks);
 			bzc = (int)(b % nchunks) << 5;
 			const long long t = b / nchunks;
 			by0 = (int)(t % groups_per_x) * CPW;
@@ -247,6 +275,8 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 	}
 	const unsigned free_mask = __ballot_sync(0xffffffffu, cls == kFree);
 	unsigned todo = __ballot_sync(0xffffffffu, cls != kCull);
+	if (f.debug & 1) todo = 0;            // ablation: classification only
+	if (f.debug & 4) todo &= free_mask;   // ablation: FREE bricks only
 
 	// ---- stage B: cooperative update of the surviving bricks --------------------------------
 	// Software pipeline: the SDF / weight quads of brick i+1 are requested before brick i is
@@ -276,33 +306,41 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 		const bool ok = ok_n;
 		const int x = x_n, y = y_n, zl = zl_n;
 		if (todo) issue(__ffs(todo) - 1);  // prefetch the next brick
-		if (!ok) continue;
 		F sn = sv;
 		float *sp = reinterpret_cast<float *>(&sn);
 		int *w = reinterpret_cast<int *>(&wv);
-		if ((free_mask >> s) & 1u) {
+		if ((free_mask >> s) & 1u) {  // warp-uniform
 			// FREE brick: every voxel gets diff == 1.0f (> near_gate, so no colour / histogram update)
+			if (ok) {
+				bool steady = true;
 #pragma unroll
-			for (int k = 0; k < VEC; k++) {
-				sp[k] = sdf_update(sp[k], w[k], 1.0f);
-				w[k] += 1;
+				for (int k = 0; k < VEC; k++) steady &= (sp[k] == 1.0f) & ((unsigned)w[k] < (1u << 24));
+#pragma unroll
+				for (int k = 0; k < VEC; k++) {
+					if (!steady) sp[k] = sdf_update(sp[k], w[k], 1.0f);
+					w[k] += 1;
+				}
+				nU += VEC;
+				*reinterpret_cast<I *>(p.wt + v0) = wv;
+				if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 			}
-			nU += VEC;
-			*reinterpret_cast<I *>(p.wt + v0) = wv;
-			if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 			continue;
 		}
 		// MIXED brick: per-voxel evaluation (tsdf.cu:30-68), phased so that the independent loads of
 		// the lane's VEC voxels are in flight together instead of one dependent miss after another.
+		// All 32 lanes stay converged through this block (the surface queue below uses warp ballots).
 		const float px = __fmaf_rn((float)x, g.vx, g.sx);
 		const float py = __fmaf_rn((float)y, g.vy, g.sy);
 		const float h0 = affine_hoist(px, py, f.E[0], f.E[1]);
 		const float h1 = affine_hoist(px, py, f.E[4], f.E[5]);
 		const float h2 = affine_hoist(px, py, f.E[8], f.E[9]);
-		float czv[VEC];
+		// The common case of every step is straight-line code; the rare exact re-evaluations are
+		// collected in bit masks and handled after the loop by out-of-line helpers, so the hot path
+		// carries no per-voxel branches.
+		float czv[VEC], diffv[VEC], sxv[VEC], syv[VEC], szv[VEC];
 		int img[VEC];
-		bool inb[VEC];
-		// phase 1: projection -> pixel (no memory)
+		unsigned inb = 0, inexact = 0;
+		// phase 1: projection -> pixel (no memory).  tsdf.cu:30-46
 #pragma unroll
 		for (int k = 0; k < VEC; k++) {
 			const float pz = __fmaf_rn((float)(g.z0 + zl + k), g.vz, g.sz);
@@ -312,80 +350,93 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 			const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, czv[k]);
 			const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, czv[k]);
 			const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, czv[k]);
-			const int ix = __float2int_rd(__fdiv_rn(sx, sz)), iy = __float2int_rd(__fdiv_rn(sy, sz));
-			inb[k] = ix >= 0 && ix < f.W && iy >= 0 && iy < f.H;  // tsdf.cu:46
-			img[k] = inb[k] ? iy * f.W + ix : 0;
+			sxv[k] = sx; syv[k] = sy; szv[k] = sz;
+			// ix = floor(RN(sx/sz)) without the IEEE divide: see pixel_floor_is_safe()
+			float r;
+			asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(sz));
+			const float qx = __fmul_rn(sx, r), qy = __fmul_rn(sy, r);
+			if (!pixel_floor_is_safe(qx, qy)) inexact |= 1u << k;
+			const int ix = __float2int_rd(qx), iy = __float2int_rd(qy);
+			if ((unsigned)ix < (unsigned)f.W && (unsigned)iy < (unsigned)f.H) inb |= 1u << k;
+			img[k] = iy * f.W + ix;
 		}
+		if (inexact) {  // ~1 voxel in 10^4: decide with the exact IEEE divides (out-of-line helper)
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				if ((inexact >> k) & 1u) {
+					const int ix = __float2int_rd(exact_div(sxv[k], szv[k])), iy = __float2int_rd(exact_div(syv[k], szv[k]));
+					const bool in = (unsigned)ix < (unsigned)f.W && (unsigned)iy < (unsigned)f.H;
+					inb = (inb & ~(1u << k)) | ((in ? 1u : 0u) << k);
+					img[k] = iy * f.W + ix;
+				}
+		}
+		if (!ok) inb = 0;
 		// phase 2: depth (metres, = depth/5000.f computed once per pixel by K0), all VEC loads at once
 		float dm[VEC];
 #pragma unroll
-		for (int k = 0; k < VEC; k++) dm[k] = __ldg(f.depth_m + img[k]);
+		for (int k = 0; k < VEC; k++) dm[k] = __ldg(f.depth_m + (((inb >> k) & 1u) ? img[k] : 0));
 		// phase 3: tsdf.cu:48-52
 		float nd[VEC];
-		unsigned touched = 0, surface = 0;
+		unsigned touched = 0, band = 0, surface = 0;
 #pragma unroll
 		for (int k = 0; k < VEC; k++) {
-			const float diff = __fadd_rn(dm[k], -czv[k]);
+			diffv[k] = __fadd_rn(dm[k], -czv[k]);
 			// depth == 0 <=> dm == 0;  "diff <= -miu" rejects, NaN survives as in the reference
-			const bool t = inb[k] && dm[k] != 0.f && !(diff <= -g.miu);
-			// miu/miu == 1.0f exactly, so the clamped case needs no divide
-			nd[k] = (diff > g.miu) ? 1.0f : __fdiv_rn(diff, g.miu);
-			if (t) {
+			if (((inb >> k) & 1u) && dm[k] != 0.f && !(diffv[k] <= -g.miu)) {
 				touched |= 1u << k;
-				if (nd[k] < f.near_gate) surface |= 1u << k;  // tsdf.cu:57
+				if (!(diffv[k] > g.miu)) band |= 1u << k;  // inside the truncation band: needs diff/miu
+			}
+			nd[k] = 1.0f;  // miu/miu == 1.0f exactly: the clamped case needs no divide
+		}
+		if (band) {
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				if ((band >> k) & 1u) {
+					nd[k] = exact_div(diffv[k], g.miu);
+					if (nd[k] < f.near_gate) surface |= 1u << k;  // tsdf.cu:57
+				}
+		}
+		// near-surface voxels (tsdf.cu:57-62: colour running mean + histogram increment) are deferred to
+		// a per-warp queue and processed 32 at a time by all lanes (drain_surface_queue), instead of a
+		// few lanes chasing label -> histogram loads one voxel after another
+		if ((f.debug & 2)) surface = 0;      // ablation: no near-surface updates
+		if (__any_sync(0xffffffffu, surface != 0)) {
+#pragma unroll
+			for (int k = 0; k < VEC; k++) {
+				const bool sf = (surface >> k) & 1u;
+				const unsigned m = __ballot_sync(0xffffffffu, sf);
+				if (sf) {
+					const int slot = qcount + __popc(m & ((1u << lane) - 1u));
+					const unsigned long long vv = (unsigned long long)(v0 + k);
+					q[slot] = make_uint4((unsigned)vv, (unsigned)(vv >> 32), (unsigned)img[k], (unsigned)w[k]);
+				}
+				qcount += __popc(m);
 			}
 		}
-		if (!touched) continue;
-		if (surface) {
-			// colour running mean + histogram increment (tsdf.cu:57-62); gather first, then apply
-			if (VEC == 4) {
-				uint32_t *cptr = reinterpret_cast<uint32_t *>(p.color + v0 * 3);  // v0 % 4 == 0 -> 4-byte aligned
-				uint32_t cw[3] = {cptr[0], cptr[1], cptr[2]};
-				uint32_t hv[VEC] = {}, lab[VEC] = {};
-				uint32_t src[VEC] = {};
+		if (touched) {
+			// steady state of free space: sdf == 1.0f, diff == 1.0f, (1*w + 1)/(w+1) == 1.0f exactly -> only w changes
+			bool steady = true;
 #pragma unroll
-				for (int k = 0; k < VEC; k++)
-					if ((surface >> k) & 1u) {
-						const uint8_t *sp3 = f.rgb + (size_t)img[k] * 3;
-						src[k] = (uint32_t)__ldg(sp3) | ((uint32_t)__ldg(sp3 + 1) << 8) | ((uint32_t)__ldg(sp3 + 2) << 16);
-						if (LABELS) {
-							lab[k] = __ldg(f.mask + img[k]);
-							if ((int)lab[k] < p.bins) hv[k] = p.hist[(v0 + k) * (size_t)p.bins + lab[k]];
-						}
-					}
-				uint8_t *cb = reinterpret_cast<uint8_t *>(cw);
+			for (int k = 0; k < VEC; k++)
+				if ((touched >> k) & 1u) steady &= (sp[k] == 1.0f) & (nd[k] == 1.0f) & ((unsigned)w[k] < (1u << 24));
 #pragma unroll
-				for (int k = 0; k < VEC; k++)
-					if ((surface >> k) & 1u) {
-						const int wk = w[k];
-#pragma unroll
-						for (int c = 0; c < 3; c++)
-							cb[k * 3 + c] = (uint8_t)(((int)cb[k * 3 + c] * wk + (int)((src[k] >> (8 * c)) & 0xffu)) / (wk + 1));
-						if (LABELS) {
-							if ((int)lab[k] < p.bins) p.hist[(v0 + k) * (size_t)p.bins + lab[k]] = hv[k] + 1u;
-							else atomicOr(err, 1u);
-						}
-						nS++;
-					}
-				cptr[0] = cw[0]; cptr[1] = cw[1]; cptr[2] = cw[2];
-			} else {
-#pragma unroll
-				for (int k = 0; k < VEC; k++)
-					if ((surface >> k) & 1u) {
-						update_surface_voxel<LABELS>(p, f, v0 + k, w[k], img[k], err);
-						nS++;
-					}
-			}
+			for (int k = 0; k < VEC; k++)
+				if ((touched >> k) & 1u) {
+					if (!steady) sp[k] = sdf_update(sp[k], w[k], nd[k]);  // tsdf.cu:56
+					w[k] += 1;                                             // tsdf.cu:68
+				}
+			nU += __popc(touched);
+			*reinterpret_cast<I *>(p.wt + v0) = wv;
+			if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 		}
-#pragma unroll
-		for (int k = 0; k < VEC; k++)
-			if ((touched >> k) & 1u) {
-				sp[k] = sdf_update(sp[k], w[k], nd[k]);  // tsdf.cu:56
-				w[k] += 1;                                // tsdf.cu:68
-				nU++;
-			}
-		*reinterpret_cast<I *>(p.wt + v0) = wv;
-		if (!same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
+		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another brick: drain
+			nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
+			qcount = 0;
+		}
+	}
+	if (qcount) {
+		nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
+		qcount = 0;
 	}
 	}  // batch loop
 

@@ -277,6 +277,7 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	f.cull_t = tt;
 	f.cull_k2 = k2;
 	f.cull_slack0 = 1.f + 1e-3f * std::max(k0, k1) / std::max(k2, 1e-20f);
+	f.debug = getenv("SFM_DEBUG_ABLATE") ? atoi(getenv("SFM_DEBUG_ABLATE")) : 0;
 	return f;
 }
 
@@ -313,6 +314,12 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	const int cpw = vec4 ? 4 : 1;
 	const long long nbricks = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw) * ((v->g.nz + 31) / 32);
 	const long long blocks = (nbricks + 31) / 32;  // number of 32-brick batches
+	{  // brick permutation multiplier ~ 0.618 * nbricks, coprime with nbricks
+		auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
+		long long m = (long long)(0.6180339887 * (double)nbricks) | 1;
+		while (m > 1 && gcd(m, nbricks) != 1) m -= 2;
+		v->g.brick_mul = (getenv("SFM_NO_PERMUTE") || m < 1) ? 1 : m;
+	}
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
 	if (vec4) {
@@ -587,6 +594,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		return fail(SFM_ERR_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
 			"; the kernels are built for sm_100a only and there is no fallback");
 	CU(cudaSetDevice(desc->device));
+	if (const char *g = getenv("SFM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
 
 	sfm_volume *v = new sfm_volume();
 	v->desc = *desc;

@@ -21,6 +21,7 @@ struct VolGeom {
 	float ex, ey, ez;  // vol_end_
 	float vx, vy, vz;  // vol_res_
 	float miu;
+	long long brick_mul;  // multiplier of K1's brick permutation (coprime with the brick count; 1 = identity)
 	int fastdiv;  // bit a set: dividing by voxel[a] may use the invariant-divisor sequence (k_raymarch.cuh)
 };
 
@@ -48,6 +49,7 @@ struct FrameView {
 	float cull_t;       // max_r |E[r][3]|
 	float cull_k2;      // |K20|+|K21|+|K22|
 	float cull_slack0;  // constant pixel slack
+	int debug;          // ablation switches for profiling (0 in production)
 };
 
 // dot(float4 row,(p,1)) as the reference compiles it (helper_math.h:1249-1252; tsdf.cu:31-33):
