@@ -48,7 +48,8 @@ typedef enum {
 
 enum {
 	SFM_FLAG_NO_CULL = 1,      /* visit every voxel (disables exact brick culling; same results) */
-	SFM_FLAG_NO_TMA = 2,       /* read frame images through the read-only path instead of TMA-staged tiles */
+	SFM_FLAG_NO_TMA = 2,       /* read the per-frame depth tile grids through L1 instead of staging them into
+	                              shared memory with a TMA bulk copy (cp.async.bulk)                      */
 	SFM_FLAG_SYNC_EVERY_CALL = 4 /* cudaStreamSynchronize before returning from every call        */
 };
 

@@ -122,7 +122,7 @@ __device__ __forceinline__ bool same_bits(const float &a, const float &b) {
 
 enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
 
-constexpr int kQueue = 256;  // per-warp capacity of the deferred near-surface queue (>= 2 bricks of 128 voxels)
+constexpr int kQueue = 160;  // per-warp capacity of the deferred near-surface queue (one brick = 128 voxels, drained at >= 32)
 
 // Colour running mean + histogram increment (tsdf.cu:57-62) for the queued near-surface voxels, one
 // voxel per lane: the label -> histogram-bin dependent loads of 32 voxels are in flight together.
@@ -163,8 +163,8 @@ __device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const Fram
 }
 
 // Stage A: classify one brick (x, columns y0..ylast, local z zc0..zc1).
-__device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, int x, int y0, int ylast,
-	int zc0, int zc1)
+__device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
+	const uint16_t *tilemin, int x, int y0, int ylast, int zc0, int zc1)
 {
 	const float px = __fmaf_rn((float)x, g.vx, g.sx);
 	float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
@@ -210,8 +210,8 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 	unsigned dmax = 0, dmin = 0xffffu;
 	for (int ty = ty0; ty <= ty1; ty++)
 		for (int tx = tx0; tx <= tx1; tx++) {
-			dmax = max(dmax, (unsigned)__ldg(f.tilemax + ty * f.TW + tx));
-			dmin = min(dmin, (unsigned)__ldg(f.tilemin + ty * f.TW + tx));
+			dmax = max(dmax, (unsigned)tilemax[ty * f.TW + tx]);
+			dmin = min(dmin, (unsigned)tilemin[ty * f.TW + tx]);
 		}
 	if (dmax == 0) return kCull;  // only invalid depth under the brick
 	if (szmin > 0.f) {
@@ -228,7 +228,7 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 	return kMixed;
 }
 
-template <int VEC, bool LABELS, bool CULL>
+template <int VEC, bool LABELS, bool CULL, bool TMA_TILES>
 __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, FrameView f,
 	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
 {
@@ -246,9 +246,38 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 	// warp that lands on culled space immediately moves on instead of idling in a resident block.
 	const long long nbatches = (nbricks + 31) >> 5;
 	unsigned nU = 0, nS = 0;
-	__shared__ uint4 queue_mem[8][kQueue];  // per-warp deferred near-surface voxels: {voxel lo, hi, pixel, weight}
-	uint4 *q = queue_mem[warp];
+	// dynamic shared memory: [8 warps x kQueue deferred near-surface voxels {voxel lo, hi, pixel, weight}]
+	//                        [tile grid: max depth | min depth]  <- staged once per block by a TMA bulk copy
+	extern __shared__ __align__(128) unsigned char smem_dyn[];
+	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
+	const uint16_t *s_tilemax = TMA_TILES ? reinterpret_cast<const uint16_t *>(smem_dyn + 8 * kQueue * sizeof(uint4)) : f.tilemax;
+	const uint16_t *s_tilemin = TMA_TILES ? s_tilemax + f.TW * f.TH : f.tilemin;
 	int qcount = 0;  // warp-uniform
+	if (CULL && TMA_TILES) {
+		// (SFM_FLAG_NO_TMA reads the grids through L1 instead; measured equal within noise.  The shared
+		// memory budget matters more: at 52 KB per block a fourth block no longer fits next to the L1
+		// carve-out and the kernel gets 27 % slower, which is why the surface queue is only 160 deep.)
+		// cp.async.bulk (TMA, SASS: UBLKCP) global -> shared, completion on an mbarrier; the persistent
+		// block does this once and then serves every tile query of its batches from shared memory
+		__shared__ __align__(8) unsigned long long tile_bar;
+		const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dyn + 8 * kQueue * sizeof(uint4));
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(f.tile_bytes) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				::"r"(dst), "l"(f.tilemax), "r"(f.tile_bytes), "r"(bar) : "memory");
+		}
+		unsigned done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				: "=r"(done) : "r"(bar) : "memory");
+		}
+	}
 	for (;;) {
 	long long batch = 0;
 	if (lane == 0) batch = atomicAdd(work_counter, 1u);
@@ -270,7 +299,7 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 			const long long t = b / nchunks;
 			by0 = (int)(t % groups_per_x) * CPW;
 			bx = (int)(t / groups_per_x);
-			cls = CULL ? classify_brick(f, g, bx, by0, min(by0 + CPW - 1, g.Dy - 1), bzc, min(bzc + 31, g.nz - 1)) : kMixed;
+			cls = CULL ? classify_brick(f, g, s_tilemax, s_tilemin, bx, by0, min(by0 + CPW - 1, g.Dy - 1), bzc, min(bzc + 31, g.nz - 1)) : kMixed;
 		}
 	}
 	const unsigned free_mask = __ballot_sync(0xffffffffu, cls == kFree);

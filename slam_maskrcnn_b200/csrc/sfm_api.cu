@@ -110,7 +110,8 @@ struct sfm_volume {
 	unsigned long long *h_stat_ring = nullptr;   // pinned, kStatRing x 2*kStatSlots
 	cudaEvent_t ev_stat[kStatRing] = {};
 	uint64_t stat_tickets = 0;
-	uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;
+	uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
+	size_t tile_bytes = 0;
 	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
 	uint32_t *d_err = nullptr;
@@ -259,6 +260,7 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	f.mask = (const uint8_t *)d_mask;
 	f.tilemax = v->d_tilemax;
 	f.tilemin = v->d_tilemin;
+	f.tile_bytes = (unsigned)v->tile_bytes;
 	f.depth_m = v->d_depth_m;
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
@@ -281,23 +283,31 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	return f;
 }
 
-template <int VEC, bool LABELS, bool CULL>
-void launch_integrate2(sfm_volume *v, const FrameView &f, long long nbatches) {
+template <int VEC, bool LABELS, bool CULL, bool TMA_TILES>
+void launch_integrate3(sfm_volume *v, const FrameView &f, long long nbatches) {
 	// persistent grid: one resident wave (occupancy x SM count), never more blocks than batches need
+	// dynamic shared memory: the per-warp surface queues (+ the TMA-staged tile grids when enabled)
+	const size_t smem = 8 * kQueue * sizeof(uint4) + (TMA_TILES ? v->tile_bytes : 0);
 	static int per_sm = 0;
-	if (!per_sm) {
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrate_kernel<VEC, LABELS, CULL>, 256, 0) != cudaSuccess || per_sm < 1)
-			per_sm = 4;
+	static size_t smem_set = 0;
+	if (!per_sm || smem_set != smem) {
+		cudaFuncSetAttribute(integrate_kernel<VEC, LABELS, CULL, TMA_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrate_kernel<VEC, LABELS, CULL, TMA_TILES>, 256, smem) != cudaSuccess || per_sm < 1)
+			per_sm = 1;
+		smem_set = smem;
 	}
 	const long long want = (nbatches + 7) / 8;
 	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));
-	integrate_kernel<VEC, LABELS, CULL><<<blocks, 256, 0, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err, v->d_work);
+	integrate_kernel<VEC, LABELS, CULL, TMA_TILES><<<blocks, 256, smem, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err, v->d_work);
 }
 
 template <int VEC, bool LABELS>
 void launch_integrate(sfm_volume *v, const FrameView &f, bool cull, long long nbatches) {
-	if (cull) launch_integrate2<VEC, LABELS, true>(v, f, nbatches);
-	else launch_integrate2<VEC, LABELS, false>(v, f, nbatches);
+	const bool tma = (v->desc.flags & SFM_FLAG_NO_TMA) == 0;
+	if (cull) {
+		if (tma) launch_integrate3<VEC, LABELS, true, true>(v, f, nbatches);
+		else launch_integrate3<VEC, LABELS, true, false>(v, f, nbatches);
+	} else launch_integrate3<VEC, LABELS, false, false>(v, f, nbatches);
 }
 
 // K0 + K1 on device-resident frame images
@@ -318,7 +328,9 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 		auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
 		long long m = (long long)(0.6180339887 * (double)nbricks) | 1;
 		while (m > 1 && gcd(m, nbricks) != 1) m -= 2;
-		v->g.brick_mul = (getenv("SFM_NO_PERMUTE") || m < 1) ? 1 : m;
+		// measured (round 1): the permutation balances the batches but costs image-cache locality and is
+		// 3 % slower overall, so it is opt-in
+		v->g.brick_mul = (getenv("SFM_PERMUTE_BRICKS") && m >= 1) ? m : 1;
 	}
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
@@ -653,8 +665,10 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	v->d_mask = v->d_frame[0] + npx * 5;
 	CU_OR_DESTROY(cudaMallocHost(&v->h_stat_ring, (size_t)sfm_volume::kStatRing * 2 * kStatSlots * 8));
 	for (int i = 0; i < sfm_volume::kStatRing; i++) CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_stat[i], cudaEventDisableTiming));
-	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, (size_t)v->TW * v->TH * 2));
-	CU_OR_DESTROY(cudaMalloc(&v->d_tilemin, (size_t)v->TW * v->TH * 2));
+	v->tile_bytes = (((size_t)v->TW * v->TH * 4) + 15) / 16 * 16;
+	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, v->tile_bytes));
+	CU_OR_DESTROY(cudaMemset(v->d_tilemax, 0, v->tile_bytes));
+	v->d_tilemin = v->d_tilemax + (size_t)v->TW * v->TH;
 	CU_OR_DESTROY(cudaMalloc(&v->d_depth_m, npx * 4));
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
@@ -701,7 +715,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->h_stat_ring) cudaFreeHost(v->h_stat_ring);
 	for (int i = 0; i < sfm_volume::kStatRing; i++) if (v->ev_stat[i]) cudaEventDestroy(v->ev_stat[i]);
 	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
-	cudaFree(v->d_tilemax); cudaFree(v->d_tilemin); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
+	cudaFree(v->d_tilemax); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
 	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);

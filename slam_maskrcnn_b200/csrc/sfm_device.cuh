@@ -39,6 +39,7 @@ struct FrameView {
 	const uint8_t *mask;
 	const uint16_t *tilemax;  // [TH][TW] max depth per kTile x kTile tile
 	const uint16_t *tilemin;  // [TH][TW] min depth per tile, invalid (0) included: > 0 <=> no hole in the tile
+	unsigned tile_bytes;      // bytes of [tilemax | tilemin] (contiguous, multiple of 16) for the TMA bulk copy
 	const float *depth_m;     // [H][W] depth/depth_scale in f32 (IEEE divide), 0 = invalid
 	int W, H, TW, TH;
 	float E[12];  // rows 0..2 of extrinsic2init (row-major 3x4)

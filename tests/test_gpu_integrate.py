@@ -135,3 +135,13 @@ def test_full_size_frame_256_matches_reference_kernel():
     assert_planes_equal(ours, ref, "256^3 vs reference tsdf_kernel")
     u = sum(u for u, _ in stats)
     assert 0.03 < u / (3 * 256 ** 3) < 0.4
+
+
+def test_tma_staged_tile_grids_are_exact():
+    """Tile grids staged into shared memory by cp.async.bulk (default) vs read through L1 (SFM_FLAG_NO_TMA)."""
+    from slam_maskrcnn_b200 import FLAG_NO_TMA
+    sc = Scenario(dims=(96, 96, 96), bins=16, frames=4, yaw_step_deg=4.0)
+    a, sa = run_ours(sc, flags=0)
+    b, sb = run_ours(sc, flags=FLAG_NO_TMA)
+    assert_planes_equal(a, b, "TMA tiles vs L1 tiles")
+    assert sa == sb
