@@ -430,6 +430,22 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 		// few lanes chasing label -> histogram loads one voxel after another
 		if ((f.debug & 2)) surface = 0;      // ablation: no near-surface updates
 		if (__any_sync(0xffffffffu, surface != 0)) {
+			if (surface) {
+				// surface-block map (Planes::occ): idempotent byte stores, no atomics.  A lane's VEC voxels
+				// share (x, y) and lie in one 8-block along z when VEC == 4; the low-face neighbours are
+				// marked too when a voxel sits on a block boundary (it is the +1 tap of the block before).
+#pragma unroll
+				for (int k = 0; k < VEC; k += (VEC == 4 ? 4 : 1)) {
+					const int zz = zl + k;
+					const int blk = ((x >> 3) * p.oby + (y >> 3)) * p.obz + (zz >> 3);
+					const int fx = ((x & 7) == 0 && x > 0) ? 1 : 0, fy = ((y & 7) == 0 && y > 0) ? 1 : 0;
+					const int fz = ((zz & 7) == 0 && zz > 0 && (VEC == 1 || (surface & 1u))) ? 1 : 0;
+					for (int dx = 0; dx <= fx; dx++)
+						for (int dy = 0; dy <= fy; dy++)
+							for (int dz = 0; dz <= fz; dz++)
+								p.occ[blk - dx * p.oby * p.obz - dy * p.obz - dz] = 1;
+				}
+			}
 #pragma unroll
 			for (int k = 0; k < VEC; k++) {
 				const bool sf = (surface >> k) & 1u;

@@ -117,6 +117,7 @@ struct sfm_volume {
 	uint32_t *d_err = nullptr;
 	unsigned *d_work = nullptr;
 	int num_sms = 148;
+	size_t occ_bytes = 0;
 	uint8_t *d_palette = nullptr;
 	uint8_t *d_lut = nullptr;
 	// pinned staging (host), double buffered
@@ -197,6 +198,7 @@ int reset_planes(sfm_volume *v) {
 	CU(cudaMemsetAsync(v->planes.wt, 0, v->nvox * 4, v->stream));
 	CU(cudaMemsetAsync(v->planes.color, 0, v->nvox * 3, v->stream));
 	if (v->bins > 0) CU(cudaMemsetAsync(v->planes.hist, 0, v->nvox * 4 * (size_t)v->bins, v->stream));
+	CU(cudaMemsetAsync(v->planes.occ, 0, v->occ_bytes, v->stream));
 	v->n_obs = 0;
 	v->num_objs = 0;
 	return SFM_OK;
@@ -379,6 +381,12 @@ RayVol make_ray_vol(const sfm_volume *v) {
 	V.hist = v->planes.hist;
 	V.bins = v->bins;
 	V.g = v->g;
+	// skipping is only sound while every value outside the surface blocks stays above the fine-step
+	// threshold voxel.x/2 (and positive): those values are miu (unobserved) or >= near_gate
+	const bool skip_ok = v->g.miu > v->g.vx && v->desc.near_gate > v->g.vx && v->g.vx > 0.f && !getenv("SFM_NO_SKIP");
+	V.occ = skip_ok ? v->planes.occ : nullptr;
+	V.oby = v->planes.oby;
+	V.obz = v->planes.obz;
 	return V;
 }
 
@@ -652,6 +660,14 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->planes.color, v->nvox * 3));
 	if (v->bins > 0) CU_OR_DESTROY(cudaMalloc(&v->planes.hist, v->nvox * 4 * (size_t)v->bins));
 	v->planes.bins = v->bins;
+	{  // surface-block map, see Planes::occ
+		const int obx = (v->g.Dx + 7) / 8;
+		v->planes.oby = v->g.oby = (v->g.Dy + 7) / 8;
+		v->planes.obz = v->g.obz = (v->g.nz + 7) / 8;
+		v->occ_bytes = (size_t)obx * v->planes.oby * v->planes.obz;
+		CU_OR_DESTROY(cudaMalloc(&v->planes.occ, v->occ_bytes));
+		CU_OR_DESTROY(cudaMemset(v->planes.occ, 0, v->occ_bytes));
+	}
 	const size_t npx = (size_t)v->W * v->H;
 	CU_OR_DESTROY(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) {
@@ -705,7 +721,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (!v) return;
 	cudaSetDevice(v->desc.device);
 	if (v->stream) cudaStreamSynchronize(v->stream);
-	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist);
+	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist); cudaFree(v->planes.occ);
 	if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(v->d_frame[i]);
@@ -1031,6 +1047,7 @@ int sfm_upload(sfm_volume *v, int plane, const void *src, size_t bytes) {
 	if (!need || bytes != need) return fail(SFM_ERR_INVALID, "plane / size mismatch");
 	CU(cudaSetDevice(v->desc.device));
 	CU(cudaMemcpyAsync(plane_ptr(v, plane), src, need, cudaMemcpyHostToDevice, v->stream));
+	if (plane == SFM_PLANE_SDF) CU(cudaMemsetAsync(v->planes.occ, 1, v->occ_bytes, v->stream));  // arbitrary SDF: no block may be skipped
 	CU(cudaStreamSynchronize(v->stream));
 	return SFM_OK;
 }

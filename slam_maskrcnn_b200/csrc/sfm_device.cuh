@@ -21,6 +21,7 @@ struct VolGeom {
 	float ex, ey, ez;  // vol_end_
 	float vx, vy, vz;  // vol_res_
 	float miu;
+	int oby, obz;         // strides of the 8x8x8 surface-block map (see Planes::occ)
 	long long brick_mul;  // multiplier of K1's brick permutation (coprime with the brick count; 1 = identity)
 	int fastdiv;  // bit a set: dividing by voxel[a] may use the invariant-divisor sequence (k_raymarch.cuh)
 };
@@ -31,6 +32,13 @@ struct Planes {
 	uint8_t *color;
 	uint32_t *hist;
 	int bins;
+	// Surface-block map: one byte per 8x8x8 block of voxels, set (never cleared) when a voxel of the
+	// block -- or a voxel one step beyond its low faces, i.e. a trilinear tap of a sample whose floor
+	// index lies in the block -- has ever received a near-surface update (diff < near_gate).  A sample
+	// whose floor index falls in an unset block only sees SDF values in {miu} U [near_gate, 1], so the
+	// ray-marcher may skip gathering it: it can neither be a hit (f < 0) nor trigger the fine step.
+	uint8_t *occ;
+	int oby, obz;  // block-grid strides: index = (bx*oby + by)*obz + bz
 };
 
 struct FrameView {
