@@ -72,7 +72,9 @@ typedef struct {
 	int32_t slab_z0;        /* first global z plane stored by this handle                      */
 	int32_t slab_nz;        /* number of z planes stored (0 => all of dims[2])                 */
 	int32_t flags;          /* SFM_FLAG_*                                                      */
-	int32_t reserved[8];
+	int32_t own_z0;         /* sharded ray-cast: first global z plane this handle OWNS ...     */
+	int32_t own_nz;         /* ... and how many (0 => all stored planes; stored minus owned = halo) */
+	int32_t reserved[6];
 } sfm_desc;
 
 typedef struct {
@@ -166,6 +168,19 @@ int sfm_ray_flags(sfm_volume *v, uint8_t *flags, size_t n);
 /* Per-ray first-hit keys for the multi-GPU min-composite: d_keys u64[h*w] DEVICE memory,
  * key = (float_bits(t_hit) << 32) | label, or UINT64_MAX when this slab has no hit. */
 int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, void *d_keys);
+/* Sharded ray-cast over z-slab handles, exact first-hit compositing in three MIN reductions (see
+ * k_raymarch.cuh).  All buffers are DEVICE u64[h*w]; between the stages the caller all-reduces the
+ * output with MIN over the ranks (values are < 2^63, so a signed 64-bit MIN works):
+ *   stage 1: out = first coarse-step event of the samples this handle owns
+ *   stage 2: in ev1 = reduced stage-1 events; out = first fine-step hit of the owned samples
+ *   stage 3: in ev1, ev2 = reduced events; out = float_bits(t_hit) << 32 | label for the rays whose
+ *            hit sample this handle owns, SFM_NO_HIT_KEY otherwise
+ * The handle must store a halo of ceil(voxel.x/voxel.z)+2 planes beyond its owned range on both
+ * sides (except at the volume faces); sfm_shard_halo() returns that number. */
+#define SFM_NO_HIT_KEY 0x7fffffffffffffffull
+int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
+	const void *d_ev1, const void *d_ev2, void *d_out);
+int sfm_shard_halo(const float *voxel3);
 /* key image (device) -> BGR image (host) through the palette (viewer.cu:80-83). */
 int sfm_keys_to_bgr(sfm_volume *v, const void *d_keys, int w, int h, uint8_t *bgr);
 /* Viewer::show_tsdf (viewer.cu:137-179): orbit camera matrices + ray-cast. */

@@ -24,7 +24,7 @@ class Desc(C.Structure):
         ("accept_factor", C.c_float), ("depth_scale", C.c_float), ("trunc_voxels", C.c_float),
         ("near_gate", C.c_float),
         ("device", C.c_int32), ("slab_z0", C.c_int32), ("slab_nz", C.c_int32), ("flags", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("own_z0", C.c_int32), ("own_nz", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -75,6 +75,8 @@ SYMBOLS = {
     "sfm_raycast": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sfm_ray_flags": (_i, [_vp, _vp, _sz]),
     "sfm_raycast_keys_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "sfm_shard_raycast_stage": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sfm_shard_halo": (_i, [_vp]),
     "sfm_keys_to_bgr": (_i, [_vp, _vp, _i, _i, _vp]),
     "sfm_show": (_i, [_vp, _f, _f, _i, _i, _vp]),
     "sfm_orbit_camera": (None, [_vp, _f, _f, _vp, _vp]),

@@ -627,6 +627,9 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	v->g.z0 = desc->slab_z0;
 	v->g.nz = desc->slab_nz > 0 ? desc->slab_nz : desc->dims[2] - desc->slab_z0;
 	if (v->g.z0 < 0 || v->g.nz <= 0 || v->g.z0 + v->g.nz > v->g.Dz) { delete v; return fail(SFM_ERR_INVALID, "bad z-slab"); }
+	v->g.own_z0 = desc->own_nz > 0 ? desc->own_z0 : v->g.z0;
+	v->g.own_nz = desc->own_nz > 0 ? desc->own_nz : v->g.nz;
+	if (v->g.own_z0 < v->g.z0 || v->g.own_z0 + v->g.own_nz > v->g.z0 + v->g.nz) { delete v; return fail(SFM_ERR_INVALID, "owned planes must lie inside the stored slab"); }
 	v->nvox = (size_t)v->g.Dx * v->g.Dy * v->g.nz;
 	memcpy(v->K, desc->K, sizeof(v->K));
 	bool kinv_given = false;
@@ -995,6 +998,34 @@ int sfm_ray_flags(sfm_volume *v, uint8_t *flags, size_t n) {
 	CU(cudaSetDevice(v->desc.device));
 	CU(cudaMemcpyAsync(flags, v->d_flags, n, cudaMemcpyDeviceToHost, v->stream));
 	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_shard_halo(const float *voxel3) {
+	if (!voxel3 || !(voxel3[2] > 0.f)) return 3;
+	return (int)ceilf(voxel3[0] / voxel3[2]) + 2;
+}
+
+int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
+	const void *d_ev1, const void *d_ev2, void *d_out)
+{
+	if (!v || !s2w16 || !c3 || !d_out || w <= 0 || h <= 0 || stage < 1 || stage > 3) return fail(SFM_ERR_INVALID, "bad argument");
+	if ((stage >= 2 && !d_ev1) || (stage == 3 && !d_ev2)) return fail(SFM_ERR_INVALID, "missing reduced events of the previous stage");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	const float vox[3] = {v->g.vx, v->g.vy, v->g.vz};
+	const int halo = sfm_shard_halo(vox);
+	const int lo_have = v->g.own_z0 - v->g.z0, hi_have = (v->g.z0 + v->g.nz) - (v->g.own_z0 + v->g.own_nz);
+	if ((v->g.own_z0 > 0 && lo_have < halo) || (v->g.own_z0 + v->g.own_nz < v->g.Dz && hi_have < halo))
+		return fail(SFM_ERR_INVALID, "sharded ray-cast needs a halo of " + std::to_string(halo) + " stored planes around the owned range");
+	RayVol V = make_ray_vol(v);
+	V.occ = nullptr;  // the replay visits every sample index
+	const RayCam cam = make_show_cam(s2w16, c3, w, h);
+	const int blocks = ray_blocks(w, h);
+	if (stage == 1) shard_stage1_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (unsigned long long *)d_out);
+	else if (stage == 2) shard_stage2_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (const unsigned long long *)d_ev1, (unsigned long long *)d_out);
+	else shard_stage3_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (const unsigned long long *)d_ev1, (const unsigned long long *)d_ev2, (unsigned long long *)d_out);
+	LAUNCH_CHECK(v);
 	return SFM_OK;
 }
 

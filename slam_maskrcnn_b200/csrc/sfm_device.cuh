@@ -17,6 +17,7 @@ constexpr int kMaxBins = 255;
 struct VolGeom {
 	int Dx, Dy, Dz;  // global volume dimensions (vol_dim_, tsdf.cuh:52)
 	int z0, nz;      // z-slab stored by this handle: global planes [z0, z0+nz)
+	int own_z0, own_nz;  // planes this handle OWNS in a sharded ray-cast (stored minus the halo)
 	float sx, sy, sz;  // vol_start_
 	float ex, ey, ez;  // vol_end_
 	float vx, vy, vz;  // vol_res_

@@ -76,15 +76,53 @@ def keys_to_int64(keys_u64):
     return torch.where(k < 0, torch.full_like(k, int(NO_HIT)), k)
 
 
-class SlabVolume:
-    """This rank's slab of a volume sharded over `world` ranks."""
+def shard_halo(voxel):
+    """Planes a slab must store beyond its owned range for the exact sharded ray-cast:
+    ceil(voxel.x / voxel.z) + 2 (previous sample one step back + trilinear tap + refinement)."""
+    return int(np.ceil(float(voxel[0]) / float(voxel[2]))) + 2
 
-    def __init__(self, dims, bins, rank, world, device=0, width=FRAME_W, height=FRAME_H, **kw):
+
+def stored_range(z0, nz, dz, halo):
+    """Owned planes [z0, z0+nz) -> stored planes including the halo, clipped to the volume."""
+    lo = max(0, z0 - halo)
+    hi = min(dz, z0 + nz + halo)
+    return lo, hi - lo
+
+
+class SlabVolume:
+    """This rank's slab of a volume sharded over `world` ranks.  With `halo` > 0 the handle stores
+    (and redundantly integrates) that many extra planes on both sides of the owned range, which is
+    what the exact sharded ray-cast needs; no halo data is ever exchanged."""
+
+    def __init__(self, dims, bins, rank, world, device=0, width=FRAME_W, height=FRAME_H, halo=0, **kw):
         from .tsdf import Volume
         self.rank, self.world = rank, world
         self.z0, self.nz = slab_range(rank, world, dims[2])
-        self.vol = Volume(dims=dims, bins=bins, width=width, height=height, device=device, slab=(self.z0, self.nz), **kw)
+        sz0, snz = stored_range(self.z0, self.nz, dims[2], halo)
+        self.vol = Volume(dims=dims, bins=bins, width=width, height=height, device=device, slab=(sz0, snz),
+                          own=(self.z0, self.nz), **kw)
         self.width, self.height = width, height
+        try:  # collectives and kernels must share a stream: run the handle on torch's current stream
+            import torch
+            if torch.cuda.is_available():
+                self.vol.set_stream(torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream)
+        except ImportError:
+            pass
+
+    def raycast_sharded(self, s2w, c, w, h, group=None):
+        """Exact sharded ray-cast: returns the composited int64 key image (CUDA tensor, identical on every rank)."""
+        import torch
+        dev = torch.device("cuda", self.vol.desc.device)
+        ev1 = torch.empty(w * h, dtype=torch.int64, device=dev)
+        ev2 = torch.empty(w * h, dtype=torch.int64, device=dev)
+        keys = torch.empty(w * h, dtype=torch.int64, device=dev)
+        self.vol.shard_raycast_stage(1, s2w, c, w, h, None, None, ev1.data_ptr())
+        composite_keys(ev1, group)
+        self.vol.shard_raycast_stage(2, s2w, c, w, h, ev1.data_ptr(), None, ev2.data_ptr())
+        composite_keys(ev2, group)
+        self.vol.shard_raycast_stage(3, s2w, c, w, h, ev1.data_ptr(), ev2.data_ptr(), keys.data_ptr())
+        composite_keys(keys, group)
+        return keys
 
     def set_bounds(self, *a, **k):
         self.vol.set_bounds(*a, **k)

@@ -37,7 +37,7 @@ class Volume:
 
     def __init__(self, dims=(256, 256, 256), bins=MAX_OBJECTS, width=640, height=480,
                  intrinsics=(520.9, 521.0, 325.1, 249.7), K=None, Kinv=None, device=0,
-                 slab=None, flags=0, **cfg):
+                 slab=None, own=None, flags=0, **cfg):
         self.lib = _lib.load()
         d = Desc()
         self.lib.sfm_desc_default(C.byref(d))
@@ -51,6 +51,8 @@ class Volume:
         if slab is not None:
             d.slab_z0, d.slab_nz = int(slab[0]), int(slab[1])
         d.flags = int(flags)
+        if own is not None:
+            d.own_z0, d.own_nz = int(own[0]), int(own[1])
         for k, val in cfg.items():
             if not hasattr(d, k):
                 raise TypeError(f"unknown sfm_desc field {k}")
@@ -193,6 +195,11 @@ class Volume:
 
     def raycast_keys_dev(self, s2w, c, w, h, d_keys):
         check(self.lib.sfm_raycast_keys_dev(self._h, _ptr(_f32(s2w, 16)), _ptr(_f32(c, 3)), w, h, C.c_void_p(d_keys)))
+
+    def shard_raycast_stage(self, stage, s2w, c, w, h, d_ev1, d_ev2, d_out):
+        check(self.lib.sfm_shard_raycast_stage(self._h, stage, _ptr(_f32(s2w, 16)), _ptr(_f32(c, 3)), w, h,
+                                               C.c_void_p(d_ev1) if d_ev1 else None, C.c_void_p(d_ev2) if d_ev2 else None,
+                                               C.c_void_p(d_out)))
 
     def keys_to_bgr(self, d_keys, w, h):
         bgr = np.empty((h, w, 3), np.uint8)
