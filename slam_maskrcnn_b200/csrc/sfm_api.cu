@@ -1018,8 +1018,7 @@ int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const 
 	const int lo_have = v->g.own_z0 - v->g.z0, hi_have = (v->g.z0 + v->g.nz) - (v->g.own_z0 + v->g.own_nz);
 	if ((v->g.own_z0 > 0 && lo_have < halo) || (v->g.own_z0 + v->g.own_nz < v->g.Dz && hi_have < halo))
 		return fail(SFM_ERR_INVALID, "sharded ray-cast needs a halo of " + std::to_string(halo) + " stored planes around the owned range");
-	RayVol V = make_ray_vol(v);
-	V.occ = nullptr;  // the replay visits every sample index
+	const RayVol V = make_ray_vol(v);
 	const RayCam cam = make_show_cam(s2w16, c3, w, h);
 	const int blocks = ray_blocks(w, h);
 	if (stage == 1) shard_stage1_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (unsigned long long *)d_out);
