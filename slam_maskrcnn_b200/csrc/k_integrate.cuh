@@ -444,6 +444,15 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 						for (int dy = 0; dy <= fy; dy++)
 							for (int dz = 0; dz <= fz; dz++)
 								p.occ[blk - dx * p.oby * p.obz - dy * p.obz - dz] = 1;
+					// coarse level (32^3 blocks), same rule
+					uint8_t *occ2 = p.occ + p.occ2_off;
+					const int blk2 = ((x >> 5) * p.oby2 + (y >> 5)) * p.obz2 + (zz >> 5);
+					const int gx = ((x & 31) == 0 && x > 0) ? 1 : 0, gy = ((y & 31) == 0 && y > 0) ? 1 : 0;
+					const int gz = ((zz & 31) == 0 && fz) ? 1 : 0;
+					for (int dx = 0; dx <= gx; dx++)
+						for (int dy = 0; dy <= gy; dy++)
+							for (int dz = 0; dz <= gz; dz++)
+								occ2[blk2 - dx * p.oby2 * p.obz2 - dy * p.obz2 - dz] = 1;
 				}
 			}
 #pragma unroll

@@ -667,7 +667,12 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		const int obx = (v->g.Dx + 7) / 8;
 		v->planes.oby = v->g.oby = (v->g.Dy + 7) / 8;
 		v->planes.obz = v->g.obz = (v->g.nz + 7) / 8;
-		v->occ_bytes = (size_t)obx * v->planes.oby * v->planes.obz;
+		const size_t bytes1 = ((size_t)obx * v->planes.oby * v->planes.obz + 15) / 16 * 16;
+		const int obx2 = (v->g.Dx + 31) / 32;
+		v->planes.oby2 = v->g.oby2 = (v->g.Dy + 31) / 32;
+		v->planes.obz2 = v->g.obz2 = (v->g.nz + 31) / 32;
+		v->planes.occ2_off = v->g.occ2_off = (unsigned)bytes1;
+		v->occ_bytes = bytes1 + (size_t)obx2 * v->planes.oby2 * v->planes.obz2;
 		CU_OR_DESTROY(cudaMalloc(&v->planes.occ, v->occ_bytes));
 		CU_OR_DESTROY(cudaMemset(v->planes.occ, 0, v->occ_bytes));
 	}

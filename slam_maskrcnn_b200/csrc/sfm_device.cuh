@@ -23,6 +23,8 @@ struct VolGeom {
 	float vx, vy, vz;  // vol_res_
 	float miu;
 	int oby, obz;         // strides of the 8x8x8 surface-block map (see Planes::occ)
+	int oby2, obz2;       // strides of the coarse 32x32x32 level of the same map
+	unsigned occ2_off;    // byte offset of the coarse level inside the map allocation
 	long long brick_mul;  // multiplier of K1's brick permutation (coprime with the brick count; 1 = identity)
 	int fastdiv;  // bit a set: dividing by voxel[a] may use the invariant-divisor sequence (k_raymarch.cuh)
 };
@@ -40,6 +42,8 @@ struct Planes {
 	// ray-marcher may skip gathering it: it can neither be a hit (f < 0) nor trigger the fine step.
 	uint8_t *occ;
 	int oby, obz;  // block-grid strides: index = (bx*oby + by)*obz + bz
+	int oby2, obz2;        // the same for the coarse level of 32x32x32 blocks, stored at occ + occ2_off
+	unsigned occ2_off;
 };
 
 struct FrameView {
