@@ -264,17 +264,58 @@ def run_ours(args):
 
     dims = tuple(args.dims) if args.dims else dims_for(n_gpus)
     bins = args.bins
-    nz = dims[2] // world
-    slab = (rank * nz, nz)
     K_steps, W_steps = args.steps, max(args.warmup, 3)
     n_pool = min(args.pool, K_steps + W_steps)
     sc, K, Kinv, place, frames = make_frames(n_pool, dims, args.hole_model)
-    vol = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=slab,
-                 flags=args.flags)
-    stream = torch.cuda.current_stream()
-    vol.set_stream(stream.cuda_stream)
-    vol.set_bounds(*place)
-    vol.synchronize()
+    # z-slab plan: equal thickness is badly balanced under brick culling (the near planes carry the
+    # free-space updates, the planes behind the surfaces nothing), so the slab boundaries follow a
+    # work profile measured on the GPU from the first frames (coarse 128^3 pre-pass, labels off)
+    from slam_maskrcnn_b200 import slabs as slabs_mod
+    if world > 1 and not args.equal_slabs:
+        def coarse_volume(cdims):
+            cv = Volume(dims=cdims, bins=0, width=640, height=480, K=K, Kinv=Kinv, device=local)
+            cv.set_bounds(place[0], place[1])
+            return cv
+        profile = slabs_mod.work_profile(coarse_volume, frames[:3], dims[2])
+        plan = slabs_mod.plan_slabs(dims[2], world, profile)
+    else:
+        plan = slabs_mod.plan_slabs(dims[2], world)
+    def make_volume(plan):
+        v = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=plan[rank], flags=args.flags)
+        v.set_stream(torch.cuda.current_stream().cuda_stream)
+        v.set_bounds(*place)
+        v.synchronize()
+        return v
+
+    vol = make_volume(plan)
+    # calibration (N > 1): the U-based profile misses what makes planes near the surfaces expensive
+    # (partially touched bricks, colour/histogram updates), so the plan is refined from measured
+    # per-rank kernel times: a few frames are integrated, the cost density of every old slab becomes
+    # time/planes, the slabs are re-planned and the volume re-allocated.  Part of set-up, not timed.
+    calib = []
+    if world > 1 and not args.equal_slabs:
+        for it in range(args.calibrate):
+            for i in range(6):
+                fr = frames[i % n_pool]
+                vol.integrate_raw(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"])
+            vol.synchronize()
+            t_mine = float(vol.integrate_times(4).mean())
+            ts = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(ts, torch.tensor([t_mine], dtype=torch.float64, device="cuda"))
+            ts = [float(t.item()) for t in ts]
+            calib.append([round(t, 4) for t in ts])
+            prof = np.concatenate([np.full(n, t / n) for (z0, n), t in zip(plan, ts)])
+            new_plan = slabs_mod.plan_slabs(dims[2], world, prof / prof.sum())
+            if new_plan == plan:
+                break
+            plan = new_plan
+            vol.close()
+            vol = make_volume(plan)
+        # start the measurement from a clean volume
+        vol.close()
+        vol = make_volume(plan)
+    slab = plan[rank]
+    nz = slab[1]
 
     # frames: packed [depth | colour | mask | pose] byte buffers, pinned on the host and resident in HBM
     npx = 640 * 480
@@ -371,6 +412,13 @@ def run_ours(args):
     U, S = vol.frame_stats()
     k1_ms = vol.integrate_times(min(K_steps, 2048)).astype(np.float64)
     k1_ms_max = max_over_ranks(float(k1_ms.mean()))
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([float(k1_ms.mean()), float(U) / K_steps, float(S) / K_steps, float(nz)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": i, "kernel_ms": round(float(t[0]), 4), "U_per_step": int(t[1]), "S_per_step": int(t[2]), "planes": int(t[3])}
+                    for i, t in enumerate(allr)]
 
     # ---- end-to-end region (host buffers, H2D + result D2H every step) ----------------------
     for i in range(3):
@@ -427,7 +475,7 @@ def run_ours(args):
     sampler.join(timeout=1.0)
 
     n_vox_rank = dims[0] * dims[1] * nz
-    n_vox_total = n_vox_rank * world
+    n_vox_total = dims[0] * dims[1] * dims[2]
     value = n_vox_total * K_steps / (t_dev_ms * 1e-3)
     e2e_value = n_vox_total * K_steps / (t_e2e_ms * 1e-3)
     # roofline of the dominant kernel (K1) on this rank: algorithmic bytes / K1 event time
@@ -458,7 +506,10 @@ def run_ours(args):
             "steps": K_steps, "warmup": W_steps, "ms_per_step": t_dev_ms / K_steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, dims), "dims": list(dims), "bins": bins,
-                       "voxels_per_gpu": n_vox_rank, "frame_pool": n_pool,
+                       "voxels_per_gpu": n_vox_total // world, "z_slabs": [list(p) for p in plan],
+                       "slab_plan": "equal thickness" if (world == 1 or args.equal_slabs) else "boundaries from a GPU work profile of the first 3 frames (coarse 128^3 pre-pass), refined from measured per-rank kernel times in an untimed calibration pass; slabs <= 3x the mean thickness",
+                       "slab_calibration_ms": calib,
+                       "frame_pool": n_pool,
                        "invalid_depth_model": args.hole_model + (" (15 % invalid pixels, spatially clustered like the TUM fr2 frames the reference ships)"
                                                                  if args.hole_model == "tum" else " (15 % independent per-pixel holes)"),
                        "l2": "no flush: each step reads and writes ~0.25 GB of voxel planes out of a >40 GB working set (> 126 MB L2)",
@@ -475,6 +526,7 @@ def run_ours(args):
                     "api": "sfm_integrate_raw(host pinned depth,colour,mask, pose) + sfm_stats_begin/_end (U,S of step i-1 read while step i runs)" if world == 1 else
                            "pinned host frame -> H2D on rank 0 -> ncclBroadcast -> sfm_integrate_dev + sfm_stats_begin/_end"},
             "gpu_launches": int(launches),
+            "per_rank": per_rank,
             "clocks": sampler.summary(),
             "fused_merge_path": fused,
         }
@@ -500,6 +552,8 @@ def main():
     ap.add_argument("--pool", type=int, default=12, help="distinct synthetic frames cycled over the steps")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--hole-model", default="tum", choices=["tum", "salt"])
+    ap.add_argument("--calibrate", type=int, default=3, help="N>1: re-planning iterations from measured per-rank kernel times")
+    ap.add_argument("--equal-slabs", action="store_true", help="N>1: equal-thickness z-slabs instead of the work-profile plan")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-merge", action="store_true")
     args = ap.parse_args()

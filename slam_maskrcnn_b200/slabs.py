@@ -27,6 +27,66 @@ def slab_range(rank, world, dz, align=4):
     return z0, nz
 
 
+def work_profile(volume_factory, frames, dz, coarse=128, fixed_share=0.2):
+    """Relative integration cost of every global z plane, estimated on the GPU: the given frames are
+    integrated into a coarse volume of the same physical cube (`volume_factory((coarse,)*3)` must return
+    a placed, labels-off Volume), the weight plane gives the touched voxels per z, and a constant term
+    stands for the per-brick classification every plane pays (about 20 % of the kernel at 512^3).
+    Under brick culling the near planes (free space in front of the surfaces) carry almost all of the
+    updates and the planes behind the surfaces none, so equal-thickness z-slabs are badly balanced."""
+    vol = volume_factory((coarse, coarse, coarse))
+    for fr in frames:
+        vol.integrate_raw(fr["depth"], fr["color"], None, fr["extrinsic"])
+    w = vol.download("weight").astype(np.float64).sum(axis=(0, 1))  # touched voxel-frames per coarse z plane
+    vol.close()
+    w = w / max(w.sum(), 1.0)
+    cost = fixed_share / coarse + (1.0 - fixed_share) * w
+    # resample to dz planes (piecewise constant), keep the total
+    idx = np.minimum((np.arange(dz) * coarse) // dz, coarse - 1)
+    prof = cost[idx]
+    return prof / prof.sum()
+
+
+def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
+    """Contiguous z-slabs [(z0, nz)] for `world` ranks.  Without a profile: equal thickness.  With a
+    per-plane cost profile: the partition minimising the largest slab cost subject to every slab being
+    a multiple of `align` planes and at most max_factor * dz / world planes thick (memory: the
+    histogram of a slab must fit one GPU).  Greedy sweep inside a bisection on the cost bound."""
+    if profile is None or world == 1:
+        return [slab_range(r, world, dz, align=min(align, 4)) for r in range(world)]
+    assert len(profile) == dz and dz % align == 0 and dz // align >= world
+    cost = np.asarray(profile, np.float64).reshape(dz // align, align).sum(1)
+    cost = cost / cost.sum()
+    nchunks = len(cost)
+    max_c = max(1, int(max_factor * dz / world) // align)
+    assert max_c * world >= nchunks, "max_factor too small to cover the volume"
+
+    def sweep(bound):
+        cuts, i = [0], 0
+        for r in range(world):
+            acc, n = 0.0, 0
+            remaining_slabs = world - r - 1
+            while i < nchunks and n < max_c and nchunks - i > remaining_slabs:  # leave >= 1 chunk per later slab
+                if n > 0 and acc + cost[i] > bound:
+                    break
+                acc += cost[i]
+                i += 1
+                n += 1
+            cuts.append(i)
+        return cuts if i == nchunks else None
+
+    lo, hi = 1.0 / world, 1.0
+    best = sweep(hi)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        c = sweep(mid)
+        if c is not None:
+            best, hi = c, mid
+        else:
+            lo = mid
+    return [(best[r] * align, (best[r + 1] - best[r]) * align) for r in range(world)]
+
+
 def frame_nbytes(width=FRAME_W, height=FRAME_H):
     return width * height * 6 + 64
 
@@ -94,10 +154,10 @@ class SlabVolume:
     (and redundantly integrates) that many extra planes on both sides of the owned range, which is
     what the exact sharded ray-cast needs; no halo data is ever exchanged."""
 
-    def __init__(self, dims, bins, rank, world, device=0, width=FRAME_W, height=FRAME_H, halo=0, **kw):
+    def __init__(self, dims, bins, rank, world, device=0, width=FRAME_W, height=FRAME_H, halo=0, plan=None, **kw):
         from .tsdf import Volume
         self.rank, self.world = rank, world
-        self.z0, self.nz = slab_range(rank, world, dims[2])
+        self.z0, self.nz = plan[rank] if plan is not None else slab_range(rank, world, dims[2])
         sz0, snz = stored_range(self.z0, self.nz, dims[2], halo)
         self.vol = Volume(dims=dims, bins=bins, width=width, height=height, device=device, slab=(sz0, snz),
                           own=(self.z0, self.nz), **kw)

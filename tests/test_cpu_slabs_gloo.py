@@ -98,3 +98,18 @@ def test_gloo_world2_broadcast_slabs_and_composite():
         assert p.exitcode == 0
     for r in res:
         assert all(r[1:]), f"rank {r[0]}: (bcast, slab, untouched, composite, order) = {r[1:]}"
+
+
+def test_slab_planner_balances_a_front_loaded_profile():
+    from slam_maskrcnn_b200.slabs import plan_slabs
+    dz = 1024
+    prof = np.where(np.arange(dz) < 560, 1.0, 0.0) * 0.8 / 560 + 0.2 / dz
+    for world in (2, 4, 8):
+        plan = plan_slabs(dz, world, prof)
+        assert plan[0][0] == 0 and sum(n for _, n in plan) == dz
+        assert all(plan[i][0] + plan[i][1] == plan[i + 1][0] for i in range(world - 1))
+        assert all(n % 8 == 0 and 0 < n <= 3 * dz // world for _, n in plan)
+        loads = [prof[z0:z0 + n].sum() * world for z0, n in plan]
+        equal = [prof[i * dz // world:(i + 1) * dz // world].sum() * world for i in range(world)]
+        assert max(loads) < 1.2 and max(loads) < max(equal)
+    assert plan_slabs(512, 2) == [(0, 256), (256, 256)]
