@@ -484,6 +484,12 @@ def run_ours(args):
     alg_per_launch = alg_bytes / K_steps
     peak, peak_src = measured_peaks()
     achieved = alg_per_launch / (k1_ms.mean() * 1e-3) / 1e9
+    # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    if world == 1 and tuple(dims) == (512, 512, 512) and bins == 80 and args.hole_model == "tum" and os.path.exists(tpath):
+        with open(tpath) as tf:
+            traffic = json.load(tf)["dram_bytes_per_launch"]
     U_all, S_all = sum_over_ranks(U), sum_over_ranks(S)
 
     cpu_base = None
@@ -517,7 +523,7 @@ def run_ours(args):
             "touched_voxel_updates_per_s": U_all / (t_dev_ms * 1e-3),
             "U_per_step": U_all / K_steps, "S_per_step": S_all / K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "integrate_kernel<4,true,true> (K1)",
+                         "traffic": traffic, "traffic_source": "profiles/r1_k1_traffic.json (ncu --set full, per launch)" if traffic else None, "peak_source": peak_src, "kernel": "integrate_kernel<4,true,true> (K1)",
                          "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_avg": float(k1_ms.mean()),
                          "kernel_ms_avg_max_rank": k1_ms_max, "launches_timed": n_timed,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
