@@ -50,7 +50,9 @@ enum {
 	SFM_FLAG_NO_CULL = 1,      /* visit every voxel (disables exact brick culling; same results) */
 	SFM_FLAG_NO_TMA = 2,       /* read the per-frame depth tile grids through L1 instead of staging them into
 	                              shared memory with a TMA bulk copy (cp.async.bulk)                      */
-	SFM_FLAG_SYNC_EVERY_CALL = 4 /* cudaStreamSynchronize before returning from every call        */
+	SFM_FLAG_SYNC_EVERY_CALL = 4, /* cudaStreamSynchronize before returning from every call        */
+	SFM_FLAG_GENERIC_K = 8     /* evaluate K*c with all nine terms even when K has the pinhole zero pattern
+	                              (the default drops the exact-zero terms; same results)                  */
 };
 
 /* Creation parameters.  Defaults (sfm_desc_default) are the reference's hard-coded values. */
@@ -199,10 +201,12 @@ int sfm_timer_start(sfm_volume *v);
 int sfm_timer_stop(sfm_volume *v, float *ms);
 /* Number of kernel launches issued by this handle so far. */
 uint64_t sfm_launch_count(sfm_volume *v);
-/* Device time (ms) of the integrate kernel alone (K1) for the last call / the last n calls, from
- * CUDA events the library records around each launch (ring of 2048 calls, oldest first). */
+/* Device time (ms) of the integrate step (K1a classification + K1b update, tsdf_kernel's work) for the
+ * last call / the last n calls, from CUDA events the library records around the launches (ring of 2048
+ * calls, oldest first).  _times2 splits it into the two kernels. */
 int sfm_last_integrate_ms(sfm_volume *v, float *ms);
 int sfm_integrate_times(sfm_volume *v, float *ms, int n);
+int sfm_integrate_times2(sfm_volume *v, float *ms_classify, float *ms_update, int n);
 
 /* U = voxels whose weight was incremented, S = voxels whose colour/histogram was updated, summed
  * over the integrate calls since the previous sfm_frame_stats call: the terms of the

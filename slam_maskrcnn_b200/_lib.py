@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfm_b200.so")
+# SFM_B200_LIB selects another BUILD of the same library (A/B experiments); there is still no fallback
+LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so")
 
 
 class SfmError(RuntimeError):
@@ -47,6 +48,7 @@ class MergeReport(C.Structure):
 
 FLAG_NO_CULL = 1
 FLAG_NO_TMA = 2
+FLAG_GENERIC_K = 8
 FLAG_SYNC_EVERY_CALL = 4
 PLANE_SDF, PLANE_WEIGHT, PLANE_COLOR, PLANE_HIST = 0, 1, 2, 3
 
@@ -91,6 +93,7 @@ SYMBOLS = {
     "sfm_integrate_times": (_i, [_vp, _vp, _i]),
     "sfm_frame_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_stats_begin": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "sfm_integrate_times2": (_i, [_vp, _vp, _vp, _i]),
     "sfm_stats_end": (_i, [_vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_debug_divcheck": (_i, [_f, C.c_uint, _i, _i, _f, C.POINTER(C.c_uint64)]),
     "sfm_mean_depth": (_f, [_vp, _i]),

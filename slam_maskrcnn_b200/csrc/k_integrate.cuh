@@ -23,6 +23,11 @@
 //     1.0f; an SDF quad whose bits did not change is not written back.
 //   * Per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
 //     shuffles + one spread atomic pair per warp -- they define the algorithmic bytes of the step.
+//   * Super-blocks: the unit a warp fetches is a box of kSbX x-planes x kSbG brick rows x one 32-z
+//     chunk (= 32 bricks, one per lane).  Before stage A the whole warp classifies the BOX with the
+//     same conservative test (8 corners on 8 lanes, CREDUX.F32 min/max, lane-strided tile scan):
+//     about 70 % of the boxes of a 512^3 volume are CULL and cost ~100 warp instructions instead of
+//     a full stage A; a FREE box skips the per-brick classification as well.
 #pragma once
 #include "sfm_device.cuh"
 
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restr
 	uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
 {
 	const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gtid == 0) *work_counter = 0u;  // K1's dynamic work counter
+	if (gtid < 3) work_counter[gtid] = 0u;  // WorkLists::counts: list sizes and K1b's fetch cursor
 	const int warp = gtid >> 5, lane = threadIdx.x & 31;
 	if (warp >= TW * TH) return;
 	const int ty = warp / TW, tx = warp % TW;
@@ -122,6 +127,45 @@ __device__ __forceinline__ bool same_bits(const float &a, const float &b) {
 
 enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
 
+#ifndef SFM_K1_MIN_BLOCKS
+#define SFM_K1_MIN_BLOCKS 4  // resident 256-thread blocks per SM K1 is compiled for (register cap 64)
+#endif
+
+constexpr int kSbX = 8;  // super-block: kSbX x-planes x kSbG brick rows x one 32-z chunk = 32 bricks
+constexpr int kSbG = 4;
+
+// warp-wide float min / max in one instruction (sm_100a: redux.sync.f32 -> CREDUX); NaNs are ignored
+__device__ __forceinline__ float redux_min(float v) {
+	float r;
+	asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+	return r;
+}
+__device__ __forceinline__ float redux_max(float v) {
+	float r;
+	asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+	return r;
+}
+
+// s = K[0:3,0:3] * c in the reference's compiled order (tsdf.cu:35-37 -> dot3_ref).  KCANON: the
+// intrinsic matrix has the pinhole pattern [[fx,0,cx],[0,fy,cy],[0,0,1]] (kernel.cpp:39-40,
+// tsdf.cu:137-150 can build no other).  Then the zero terms drop out bit-exactly for finite
+// inputs -- fma(cx,fx, cy*0) == RN(cx*fx), fma(cx,0, cy*fy) == RN(cy*fy), fma(cz,1, 0) == cz --
+// up to the sign of an exact zero, which neither floor(s/sz) nor the bounds test can see.
+template <bool KCANON>
+__device__ __forceinline__ void cam_to_screen(const FrameView &f, float cx, float cy, float cz, float &sx, float &sy, float &sz) {
+	if (KCANON) {
+		sx = __fmaf_rn(cz, f.K[2], __fmul_rn(cx, f.K[0]));
+		sy = __fmaf_rn(cz, f.K[5], __fmul_rn(cy, f.K[4]));
+		sz = cz;
+	} else {
+		sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
+		sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
+		sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
+	}
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int kQueue = 160;  // per-warp capacity of the deferred near-surface queue (one brick = 128 voxels, drained at >= 32)
 
 // Colour running mean + histogram increment (tsdf.cu:57-62) for the queued near-surface voxels, one
@@ -162,106 +206,171 @@ __device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const Fram
 	return done;
 }
 
-// Stage A: classify one brick (x, columns y0..ylast, local z zc0..zc1).
-__device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
-	const uint16_t *tilemin, int x, int y0, int ylast, int zc0, int zc1)
+// Projected bounds of a box of voxels: pixel bounding box of its corners, range of the homogeneous
+// and camera-space depth, magnitude bound of the camera-space coordinates (rounding-error budget).
+struct BoxBounds {
+	float umin, umax, vmin, vmax, szmin, szmax, czmin, czmax, scale_c;
+};
+
+// Second half of the conservative classification, shared by bricks (one lane each, COOP = false)
+// and super-blocks (whole warp, COOP = true: the tiles under the box are scanned lane-strided).
+// The projective map sends segments that stay on one side of the camera plane to segments, so with
+// all corners of a (convex) box strictly on one side the pixel coordinates of every voxel of the box
+// lie inside the bounding box of the projected corners (plus rounding slack), and the camera-space
+// depth, being affine, takes its extremes at corners.  Rounding-error budget: |c*| <= scale_c,
+// per-voxel error of c*, s* ~ 1e-6*scale; a box is only classified when all corners are at least
+// 1e-2*scale_sz away from the camera plane, which bounds the per-voxel pixel error by
+// ~1e-4*(Krow/K2row + |u|) -- the slack is 10x that.
+template <bool COOP>
+__device__ __forceinline__ int classify_bounds(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
+	const uint16_t *tilemin, const BoxBounds &b, int lane, int max_tiles)
 {
-	const float px = __fmaf_rn((float)x, g.vx, g.sx);
-	float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
-	float szmin = INFINITY, szmax = -INFINITY, czmin = INFINITY, czmax = -INFINITY, scale_c = 0.f;
-#pragma unroll 1
-	for (int corner = 0; corner < 4; corner++) {
-		const float py = __fmaf_rn((float)((corner & 1) ? ylast : y0), g.vy, g.sy);
-		const float pz = __fmaf_rn((float)(g.z0 + ((corner & 2) ? zc1 : zc0)), g.vz, g.sz);
-		const float cx = affine_finish(affine_hoist(px, py, f.E[0], f.E[1]), pz, f.E[2], f.E[3]);
-		const float cy = affine_finish(affine_hoist(px, py, f.E[4], f.E[5]), pz, f.E[6], f.E[7]);
-		const float cz = affine_finish(affine_hoist(px, py, f.E[8], f.E[9]), pz, f.E[10], f.E[11]);
-		const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
-		const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
-		const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
-		const float u = __fdividef(sx, sz), v = __fdividef(sy, sz);  // approximate is fine: the slack is 1e-3 relative
-		umin = fminf(umin, u); umax = fmaxf(umax, u);
-		vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-		szmin = fminf(szmin, sz); szmax = fmaxf(szmax, sz);
-		czmin = fminf(czmin, cz); czmax = fmaxf(czmax, cz);
-		// magnitude bound of the camera-space coordinates (rounding-error budget)
-		scale_c = fmaxf(scale_c, f.cull_lin * (fabsf(px) + fabsf(py) + fabsf(pz) + 1.f) + f.cull_t);
-	}
-	// The projective map is monotone along any segment that stays on one side of the camera plane,
-	// so with all four corners strictly on one side the pixel coordinates of every voxel of the
-	// brick lie inside the corner bounding box (plus rounding slack).  Rounding-error budget:
-	// |c*| <= scale_c, per-voxel error of c*, s* ~ 1e-6*scale; a brick is only classified when all
-	// corners are at least 1e-2*scale_sz away from the camera plane, which bounds the per-voxel
-	// pixel error by ~1e-4*(Krow/K2row + |u|) -- the slack is 10x that.  NaNs fail `finite`.
-	const float zguard = 1e-2f * f.cull_k2 * scale_c;
-	const bool one_side = (szmin > zguard) || (szmax < -zguard);
-	const bool finite = fabsf(umin) < 1e8f && fabsf(umax) < 1e8f && fabsf(vmin) < 1e8f && fabsf(vmax) < 1e8f &&
-		fabsf(czmin) < 1e30f && fabsf(czmax) < 1e30f;
-	if (!(one_side && finite)) return kMixed;
-	const float slack_u = f.cull_slack0 + 1e-3f * fmaxf(fabsf(umin), fabsf(umax));
-	const float slack_v = f.cull_slack0 + 1e-3f * fmaxf(fabsf(vmin), fabsf(vmax));
-	const float ulo = umin - slack_u, uhi = umax + slack_u;
-	const float vlo = vmin - slack_v, vhi = vmax + slack_v;
+	const float zguard = 1e-2f * f.cull_k2 * b.scale_c;
+	const bool one_side = (b.szmin > zguard) || (b.szmax < -zguard);
+	if (!one_side) return kMixed;
+	const float slack_u = f.cull_slack0 + 1e-3f * fmaxf(fabsf(b.umin), fabsf(b.umax));
+	const float slack_v = f.cull_slack0 + 1e-3f * fmaxf(fabsf(b.vmin), fabsf(b.vmax));
+	const float ulo = b.umin - slack_u, uhi = b.umax + slack_u;
+	const float vlo = b.vmin - slack_v, vhi = b.vmax + slack_v;
 	if (uhi < 0.f || ulo >= (float)f.W || vhi < 0.f || vlo >= (float)f.H) return kCull;  // outside the image
 	const bool inside = ulo >= 0.f && uhi < (float)f.W && vlo >= 0.f && vhi < (float)f.H;
 	const int tx0 = max(0, (int)floorf(ulo)) / kTile, tx1 = min(f.W - 1, (int)floorf(uhi)) / kTile;
 	const int ty0 = max(0, (int)floorf(vlo)) / kTile, ty1 = min(f.H - 1, (int)floorf(vhi)) / kTile;
-	if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 96) return kMixed;  // huge footprint (brick close to the camera)
+	const int tw = tx1 - tx0 + 1, nt = tw * (ty1 - ty0 + 1);
+	if (nt > max_tiles) return kMixed;  // huge footprint (box close to the camera)
 	unsigned dmax = 0, dmin = 0xffffu;
-	for (int ty = ty0; ty <= ty1; ty++)
-		for (int tx = tx0; tx <= tx1; tx++) {
-			dmax = max(dmax, (unsigned)tilemax[ty * f.TW + tx]);
-			dmin = min(dmin, (unsigned)tilemin[ty * f.TW + tx]);
+	if (COOP) {
+		for (int i = lane; i < nt; i += 32) {
+			const int r = i / tw, t = (ty0 + r) * f.TW + tx0 + (i - r * tw);
+			dmax = max(dmax, (unsigned)tilemax[t]);
+			dmin = min(dmin, (unsigned)tilemin[t]);
 		}
-	if (dmax == 0) return kCull;  // only invalid depth under the brick
-	if (szmin > 0.f) {
+		dmax = __reduce_max_sync(0xffffffffu, dmax);
+		dmin = __reduce_min_sync(0xffffffffu, dmin);
+	} else {
+		for (int ty = ty0; ty <= ty1; ty++)
+			for (int tx = tx0; tx <= tx1; tx++) {
+				dmax = max(dmax, (unsigned)tilemax[ty * f.TW + tx]);
+				dmin = min(dmin, (unsigned)tilemin[ty * f.TW + tx]);
+			}
+	}
+	if (dmax == 0) return kCull;  // only invalid depth under the box
+	if (b.szmin > 0.f) {
 		const float dmax_m = __fdiv_rn((float)dmax, f.depth_scale), dmin_m = __fdiv_rn((float)dmin, f.depth_scale);
-		const float eps = 1e-4f * (scale_c + dmax_m);
+		const float eps = 1e-4f * (b.scale_c + dmax_m);
 		// every voxel: diff = d/scale - cz <= dmax/scale - czmin + eps  =>  behind the surface band
-		if (czmin - dmax_m >= g.miu + eps) return kCull;
+		if (b.czmin - dmax_m >= g.miu + eps) return kCull;
 		// every voxel: valid pixel inside the image (no tile under the box has a hole: min > 0) and
 		// diff >= dmin/scale - czmax - eps > miu   =>  diff clamps to miu, i.e. exactly 1.0f
 		// (An exact per-pixel invalid bitmap was measured here: it lifts the FREE share from 15 % to
 		// 23 % of the surviving bricks but costs more instructions than it saves; see DESIGN.md.)
-		if (inside && dmin > 0 && dmin_m - czmax > g.miu + eps) return kFree;
+		if (inside && dmin > 0 && dmin_m - b.czmax > g.miu + eps) return kFree;
 	}
 	return kMixed;
 }
 
-template <int VEC, bool LABELS, bool CULL, bool TMA_TILES>
-__global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, FrameView f,
-	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
+// approximate projection of one box corner (classification only: the slack is 1e-3 relative)
+__device__ __forceinline__ void project_corner(const FrameView &f, float px, float py, float pz, float &u, float &v,
+	float &sz, float &cz, float &scale)
 {
-	constexpr int LPC = 32 / VEC;  // lanes per column
-	constexpr int CPW = 32 / LPC;  // columns per brick
-	using F = typename VecT<VEC>::F;
-	using I = typename VecT<VEC>::I;
+	const float cx = affine_finish(affine_hoist(px, py, f.E[0], f.E[1]), pz, f.E[2], f.E[3]);
+	const float cy = affine_finish(affine_hoist(px, py, f.E[4], f.E[5]), pz, f.E[6], f.E[7]);
+	cz = affine_finish(affine_hoist(px, py, f.E[8], f.E[9]), pz, f.E[10], f.E[11]);
+	const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, cz);
+	const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, cz);
+	sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, cz);
+	u = __fdividef(sx, sz);
+	v = __fdividef(sy, sz);
+	scale = f.cull_lin * (fabsf(px) + fabsf(py) + fabsf(pz) + 1.f) + f.cull_t;
+}
+
+// Stage A: classify one brick (x, columns y0..ylast, local z zc0..zc1), one lane.
+__device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
+	const uint16_t *tilemin, int x, int y0, int ylast, int zc0, int zc1)
+{
+	const float px = __fmaf_rn((float)x, g.vx, g.sx);
+	BoxBounds b{INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY, 0.f};
+	bool finite = true;
+#pragma unroll
+	for (int corner = 0; corner < 4; corner++) {
+		const float py = __fmaf_rn((float)((corner & 1) ? ylast : y0), g.vy, g.sy);
+		const float pz = __fmaf_rn((float)(g.z0 + ((corner & 2) ? zc1 : zc0)), g.vz, g.sz);
+		float u, v, sz, cz, scale;
+		project_corner(f, px, py, pz, u, v, sz, cz, scale);
+		b.umin = fminf(b.umin, u); b.umax = fmaxf(b.umax, u);
+		b.vmin = fminf(b.vmin, v); b.vmax = fmaxf(b.vmax, v);
+		b.szmin = fminf(b.szmin, sz); b.szmax = fmaxf(b.szmax, sz);
+		b.czmin = fminf(b.czmin, cz); b.czmax = fmaxf(b.czmax, cz);
+		b.scale_c = fmaxf(b.scale_c, scale);
+		finite &= fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
+	}
+	if (!finite) return kMixed;
+	return classify_bounds<false>(f, g, tilemax, tilemin, b, 0, 96);
+}
+
+// Whole-warp classification of a super-block: lanes 0..7 (and their copies) project the 8 corners.
+__device__ __forceinline__ int classify_superblock(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
+	const uint16_t *tilemin, int x0, int x1, int y0, int y1, int zc0, int zc1, int lane)
+{
+	const float px = __fmaf_rn((float)((lane & 1) ? x1 : x0), g.vx, g.sx);
+	const float py = __fmaf_rn((float)((lane & 2) ? y1 : y0), g.vy, g.sy);
+	const float pz = __fmaf_rn((float)(g.z0 + ((lane & 4) ? zc1 : zc0)), g.vz, g.sz);
+	float u, v, sz, cz, scale;
+	project_corner(f, px, py, pz, u, v, sz, cz, scale);
+	const bool finite = fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
+	if (!__all_sync(0xffffffffu, finite)) return kMixed;
+	BoxBounds b;
+	b.umin = redux_min(u); b.umax = redux_max(u);
+	b.vmin = redux_min(v); b.vmax = redux_max(v);
+	b.szmin = redux_min(sz); b.szmax = redux_max(sz);
+	b.czmin = redux_min(cz); b.czmax = redux_max(cz);
+	b.scale_c = redux_max(scale);
+	return classify_bounds<true>(f, g, tilemax, tilemin, b, lane, 1024);
+}
+
+// Brick work lists written by K1a and consumed by K1b.  A brick id packs (x, brick row, z chunk).
+struct WorkLists {
+	uint32_t *mixed;   // bricks that need per-voxel evaluation
+	uint32_t *free_;   // bricks whose voxels all get diff == 1.0f
+	unsigned *counts;  // [0] = #mixed, [1] = #free, [2] = K1b's fetch cursor   (zeroed by K0)
+};
+constexpr int kIdXShift = 21, kIdGShift = 10;  // id = x << 21 | row << 10 | chunk  (x, row < 2048, chunk < 1024)
+#ifndef SFM_K1_FETCH
+#define SFM_K1_FETCH 4
+#endif
+constexpr int kFetch = SFM_K1_FETCH;           // bricks a K1b warp takes per fetch
+#ifndef SFM_K1_PERMUTE
+#define SFM_K1_PERMUTE 1
+#endif
+#ifndef SFM_K1_PIPE
+#define SFM_K1_PIPE 0
+#endif
+constexpr int kSbPerBlock = 64;                // most super-blocks one K1a block classifies (sizes its shared lists)
+
+// ---------------------------------------------------------------------------------------------
+// K1a: classification.  One warp per super-block (static stride over a persistent grid): the whole
+// warp classifies the box, then -- unless the box is CULL or FREE as a whole -- each lane classifies
+// one brick.  Surviving bricks are appended to the MIXED / FREE lists with one atomic per warp and
+// list.  The tile grids are staged into shared memory once per block by a TMA bulk copy.
+// ---------------------------------------------------------------------------------------------
+template <int CPW, bool CULL, bool TMA_TILES>
+__global__ void __launch_bounds__(256) classify_kernel(VolGeom g, FrameView f, WorkLists wl)
+{
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int zq = lane % LPC, ci = lane / LPC;
 	const int nchunks = (g.nz + 31) >> 5;
 	const int groups_per_x = (g.Dy + CPW - 1) / CPW;
-	const long long nbricks = (long long)g.Dx * groups_per_x * nchunks;
-	// Persistent warps with dynamic work fetching: the grid is sized to fill the machine once and
-	// every warp pulls batches of 32 consecutive bricks from a global counter (reset by K0), so a
-	// warp that lands on culled space immediately moves on instead of idling in a resident block.
-	const long long nbatches = (nbricks + 31) >> 5;
-	unsigned nU = 0, nS = 0;
-	// dynamic shared memory: [8 warps x kQueue deferred near-surface voxels {voxel lo, hi, pixel, weight}]
-	//                        [tile grid: max depth | min depth]  <- staged once per block by a TMA bulk copy
+	const int nsby = (groups_per_x + kSbG - 1) / kSbG;
+	const unsigned nsb = (unsigned)((g.Dx + kSbX - 1) / kSbX) * (unsigned)nsby * (unsigned)nchunks;
 	extern __shared__ __align__(128) unsigned char smem_dyn[];
-	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
-	const uint16_t *s_tilemax = TMA_TILES ? reinterpret_cast<const uint16_t *>(smem_dyn + 8 * kQueue * sizeof(uint4)) : f.tilemax;
+	const uint16_t *s_tilemax = TMA_TILES ? reinterpret_cast<const uint16_t *>(smem_dyn) : f.tilemax;
 	const uint16_t *s_tilemin = TMA_TILES ? s_tilemax + f.TW * f.TH : f.tilemin;
-	int qcount = 0;  // warp-uniform
 	if (CULL && TMA_TILES) {
-		// (SFM_FLAG_NO_TMA reads the grids through L1 instead; measured equal within noise.  The shared
-		// memory budget matters more: at 52 KB per block a fourth block no longer fits next to the L1
-		// carve-out and the kernel gets 27 % slower, which is why the surface queue is only 160 deep.)
 		// cp.async.bulk (TMA, SASS: UBLKCP) global -> shared, completion on an mbarrier; the persistent
-		// block does this once and then serves every tile query of its batches from shared memory
+		// block does this once and then serves every tile query of its super-blocks from shared memory
+		// (SFM_FLAG_NO_TMA reads the grids through L1 instead)
 		__shared__ __align__(8) unsigned long long tile_bar;
 		const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
-		const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dyn + 8 * kQueue * sizeof(uint4));
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dyn);
 		if (threadIdx.x == 0) {
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -278,67 +387,145 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 				: "=r"(done) : "r"(bar) : "memory");
 		}
 	}
-	for (;;) {
-	long long batch = 0;
-	if (lane == 0) batch = atomicAdd(work_counter, 1u);
-	batch = __shfl_sync(0xffffffffu, batch, 0);
-	if (batch >= nbatches) break;
-	const long long warp_base = batch << 5;
-
-	// ---- stage A: lane-parallel classification of 32 bricks --------------------------------
-	int cls = kCull;
-	int bx = 0, by0 = 0, bzc = 0;
-	{
-		// bricks are dealt to the batches through a multiplicative permutation (g.brick_mul is coprime
-		// with nbricks): every batch samples the whole volume, so all batches carry about the same
-		// number of surviving bricks and no warp is left finishing a dense batch alone at the end
-		long long b = warp_base + lane;
-		if (b < nbricks) {
-			b = (long long)(((unsigned long long)b * (unsigned long long)g.brick_mul) % (unsigned long long)nbricks);
-			bzc = (int)(b % nchunks) << 5;
-			const long long t = b / nchunks;
-			by0 = (int)(t % groups_per_x) * CPW;
-			bx = (int)(t / groups_per_x);
-			cls = CULL ? classify_brick(f, g, s_tilemax, s_tilemin, bx, by0, min(by0 + CPW - 1, g.Dy - 1), bzc, min(bzc + 31, g.nz - 1)) : kMixed;
+	// Surviving bricks are collected in shared memory and appended to the global lists with ONE atomic
+	// per block and list: tens of thousands of atomics on a single address would serialise in L2
+	// (measured: 20 us of a 29 us kernel).  The host sizes the grid so that a block sees <= kSbPerBlock
+	// super-blocks.
+	__shared__ unsigned s_cnt[2], s_base[2];
+	uint32_t *s_mixed = reinterpret_cast<uint32_t *>(smem_dyn + (TMA_TILES ? f.tile_bytes : 0));
+	uint32_t *s_free = s_mixed + kSbPerBlock * 32;
+	if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	for (unsigned sb = blockIdx.x * 8u + warp; sb < nsb; sb += gridDim.x * 8u) {
+		// super-block -> box (z chunk fastest)
+		const int sbz = (int)(sb % (unsigned)nchunks);
+		const unsigned sbt = sb / (unsigned)nchunks;
+		const int gy0 = (int)(sbt % (unsigned)nsby) * kSbG, x0 = (int)(sbt / (unsigned)nsby) * kSbX;
+		const int zc0 = sbz << 5, zc1 = min(zc0 + 31, g.nz - 1);
+		int sbcls = kMixed;
+		if (CULL && !(f.debug & 8))
+			sbcls = classify_superblock(f, g, s_tilemax, s_tilemin, x0, min(x0 + kSbX - 1, g.Dx - 1), gy0 * CPW,
+				min((gy0 + kSbG) * CPW - 1, g.Dy - 1), zc0, zc1, lane);
+		if (sbcls == kCull) continue;
+		int cls = kCull;
+		const int bx = x0 + (lane >> 2), bg = gy0 + (lane & 3), by0 = bg * CPW;
+		if (bx < g.Dx && by0 < g.Dy)
+			cls = (!CULL) ? kMixed : (sbcls == kFree) ? kFree :
+				classify_brick(f, g, s_tilemax, s_tilemin, bx, by0, min(by0 + CPW - 1, g.Dy - 1), zc0, zc1);
+		const unsigned mm = __ballot_sync(0xffffffffu, cls == kMixed), fm = __ballot_sync(0xffffffffu, cls == kFree);
+		unsigned bm = 0, bf = 0;
+		if (lane == 0) {
+			if (mm) bm = atomicAdd(&s_cnt[0], (unsigned)__popc(mm));
+			if (fm) bf = atomicAdd(&s_cnt[1], (unsigned)__popc(fm));
 		}
+		bm = __shfl_sync(0xffffffffu, bm, 0);
+		bf = __shfl_sync(0xffffffffu, bf, 0);
+		const unsigned id = ((unsigned)bx << kIdXShift) | ((unsigned)bg << kIdGShift) | (unsigned)sbz;
+		const unsigned below = (1u << lane) - 1u;
+		if (cls == kMixed) s_mixed[bm + __popc(mm & below)] = id;
+		else if (cls == kFree) s_free[bf + __popc(fm & below)] = id;
 	}
-	const unsigned free_mask = __ballot_sync(0xffffffffu, cls == kFree);
-	unsigned todo = __ballot_sync(0xffffffffu, cls != kCull);
-	if (f.debug & 1) todo = 0;            // ablation: classification only
-	if (f.debug & 4) todo &= free_mask;   // ablation: FREE bricks only
+	__syncthreads();
+	if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(wl.counts + threadIdx.x, s_cnt[threadIdx.x]);
+	__syncthreads();
+	for (unsigned i = threadIdx.x; i < s_cnt[0]; i += blockDim.x) wl.mixed[s_base[0] + i] = s_mixed[i];
+	for (unsigned i = threadIdx.x; i < s_cnt[1]; i += blockDim.x) wl.free_[s_base[1] + i] = s_free[i];
+}
 
-	// ---- stage B: cooperative update of the surviving bricks --------------------------------
+// ---------------------------------------------------------------------------------------------
+// K1b: update.  Persistent warps pull kFetch bricks at a time from the lists (MIXED first, the
+// cheap FREE bricks last, so the tail of the kernel is made of small items) -- every warp gets the
+// same amount of work to within a few bricks, whatever the geometry of the frame.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool LABELS, bool KCANON>
+__global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
+	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
+{
+	constexpr int LPC = 32 / VEC;  // lanes per column
+	constexpr int CPW = 32 / LPC;  // columns per brick
+	using F = typename VecT<VEC>::F;
+	using I = typename VecT<VEC>::I;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int zq = lane % LPC, ci = lane / LPC;
+	unsigned nU = 0, nS = 0;
+	// dynamic shared memory: 8 warps x kQueue deferred near-surface voxels {voxel lo, hi, pixel, weight}
+	extern __shared__ __align__(128) unsigned char smem_dyn[];
+	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
+	int qcount = 0;  // warp-uniform
+	const unsigned nmixed = wl.counts[0], total = nmixed + wl.counts[1];
+	auto brick_coords = [&](unsigned id, int &x, int &y, int &zl) {  // warp-uniform id + lane offsets
+		x = (int)(id >> kIdXShift);
+		y = (int)((id >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW + ci;
+		zl = (int)((id & ((1u << kIdGShift) - 1u)) << 5) + zq * VEC;
+	};
+	auto brick_voxel = [&](int x, int y, int zl, bool ok) { return ((size_t)x * g.Dy + (ok ? y : 0)) * (size_t)g.nz + (ok ? zl : 0); };
 	// Software pipeline: the SDF / weight quads of brick i+1 are requested before brick i is
-	// evaluated, so every warp keeps two bricks' worth of 128-bit loads in flight.
+	// evaluated, so every warp keeps two bricks' worth of 128-bit loads in flight; the atomic that
+	// fetches the next group is in flight while this group is evaluated.
 	F sv_n{}; I wv_n{};
-	size_t v_n = 0;
-	int x_n = 0, y_n = 0, zl_n = 0;
-	bool ok_n = false;
-	auto issue = [&](int s) {  // executed by all 32 lanes (full-mask shuffles)
-		x_n = __shfl_sync(0xffffffffu, bx, s);
-		y_n = __shfl_sync(0xffffffffu, by0, s) + ci;
-		zl_n = __shfl_sync(0xffffffffu, bzc, s) + zq * VEC;
-		ok_n = (y_n < g.Dy) && (zl_n < g.nz);
-		v_n = ((size_t)x_n * g.Dy + (ok_n ? y_n : 0)) * (size_t)g.nz + (ok_n ? zl_n : 0);
-		if (ok_n) {
-			sv_n = *reinterpret_cast<const F *>(p.sdf + v_n);
-			wv_n = *reinterpret_cast<const I *>(p.wt + v_n);
+	auto issue = [&](unsigned id) {
+		int x, y, zl;
+		brick_coords(id, x, y, zl);
+		if ((y < g.Dy) && (zl < g.nz)) {
+			const size_t v = brick_voxel(x, y, zl, true);
+			sv_n = *reinterpret_cast<const F *>(p.sdf + v);
+			wv_n = *reinterpret_cast<const I *>(p.wt + v);
 		}
 	};
-	if (todo) issue(__ffs(todo) - 1);
-	while (todo) {
-		const int s = __ffs(todo) - 1;
-		todo &= todo - 1;
+	// list position -> brick id.  SFM_K1_PERMUTE: positions walk each list with a stride coprime to its
+	// length, so bricks that sit next to each other in space (K1a appends 32 neighbours at a time) are
+	// evaluated far apart in time: warps that chase histogram sectors and warps that do arithmetic mix
+	// on every SM instead of the whole machine hitting the same kind of brick at once.
+	const unsigned nfree = total - nmixed;
+#if SFM_K1_PERMUTE
+	const unsigned pm = (nmixed % 4093u) ? 4093u : 4091u, pf = (nfree % 4093u) ? 4093u : 4091u;
+#endif
+	auto list_at = [&](unsigned i) {
+#if SFM_K1_PERMUTE
+		if (i < nmixed) return wl.mixed[nmixed < (1u << 20) ? (i * pm) % nmixed : i];
+		const unsigned k = i - nmixed;
+		return wl.free_[nfree < (1u << 20) ? (k * pf) % nfree : k];
+#else
+		return i < nmixed ? wl.mixed[i] : wl.free_[i - nmixed];
+#endif
+	};
+	auto fetch = [&]() {  // lane 0 holds the result; broadcast when it is needed
+		unsigned b = 0;
+		if (lane == 0) b = atomicAdd(wl.counts + 2, (unsigned)kFetch);
+		return b;
+	};
+	unsigned base = __shfl_sync(0xffffffffu, fetch(), 0);
+	int n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
+	unsigned my_id = lane < n ? list_at(base + lane) : 0u;
+	unsigned next_raw = fetch();
+	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+	while (n > 0) {
+#if SFM_K1_PIPE
+	// ids of the next group: requested now, needed when the last brick of this group prefetches
+	const unsigned base_n = __shfl_sync(0xffffffffu, next_raw, 0);
+	const int n_n = base_n < total ? (int)min((unsigned)kFetch, total - base_n) : 0;
+	const unsigned id_n = lane < n_n ? list_at(base_n + lane) : 0u;
+	next_raw = fetch();
+#endif
+	for (int i = 0; i < n; i++) {
+		const unsigned id = __shfl_sync(0xffffffffu, my_id, i);
+		const bool is_free = base + i >= nmixed;  // warp-uniform
 		const F sv = sv_n;
 		I wv = wv_n;
-		const size_t v0 = v_n;
-		const bool ok = ok_n;
-		const int x = x_n, y = y_n, zl = zl_n;
-		if (todo) issue(__ffs(todo) - 1);  // prefetch the next brick
+		int x, y, zl;
+		brick_coords(id, x, y, zl);
+		const bool ok = (y < g.Dy) && (zl < g.nz);
+		const size_t v0 = brick_voxel(x, y, zl, ok);
+		// prefetch the next brick
+		if (i + 1 < n) issue(__shfl_sync(0xffffffffu, my_id, i + 1));
+#if SFM_K1_PIPE
+		else if (n_n > 0) issue(__shfl_sync(0xffffffffu, id_n, 0));
+#endif
+		if (f.debug & 1) continue;  // ablation: fetches and loads only
 		F sn = sv;
 		float *sp = reinterpret_cast<float *>(&sn);
 		int *w = reinterpret_cast<int *>(&wv);
-		if ((free_mask >> s) & 1u) {  // warp-uniform
+		if (is_free) {
 			// FREE brick: every voxel gets diff == 1.0f (> near_gate, so no colour / histogram update)
 			if (ok) {
 				bool steady = true;
@@ -355,6 +542,7 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 			}
 			continue;
 		}
+		if (f.debug & 4) continue;  // ablation: FREE bricks only
 		// MIXED brick: per-voxel evaluation (tsdf.cu:30-68), phased so that the independent loads of
 		// the lane's VEC voxels are in flight together instead of one dependent miss after another.
 		// All 32 lanes stay converged through this block (the surface queue below uses warp ballots).
@@ -376,13 +564,12 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 			const float cx = affine_finish(h0, pz, f.E[2], f.E[3]);
 			const float cy = affine_finish(h1, pz, f.E[6], f.E[7]);
 			czv[k] = affine_finish(h2, pz, f.E[10], f.E[11]);
-			const float sx = dot3_ref(f.K[0], f.K[1], f.K[2], cx, cy, czv[k]);
-			const float sy = dot3_ref(f.K[3], f.K[4], f.K[5], cx, cy, czv[k]);
-			const float sz = dot3_ref(f.K[6], f.K[7], f.K[8], cx, cy, czv[k]);
+			float sx, sy, sz;
+			cam_to_screen<KCANON>(f, cx, cy, czv[k], sx, sy, sz);
 			sxv[k] = sx; syv[k] = sy; szv[k] = sz;
 			// ix = floor(RN(sx/sz)) without the IEEE divide: see pixel_floor_is_safe()
 			float r;
-			asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(sz));
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sz));  // .ftz: one MUFU.RCP, no denormal rescaling
 			const float qx = __fmul_rn(sx, r), qy = __fmul_rn(sy, r);
 			if (!pixel_floor_is_safe(qx, qy)) inexact |= 1u << k;
 			const int ix = __float2int_rd(qx), iy = __float2int_rd(qy);
@@ -429,6 +616,13 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 		// a per-warp queue and processed 32 at a time by all lanes (drain_surface_queue), instead of a
 		// few lanes chasing label -> histogram loads one voxel after another
 		if ((f.debug & 2)) surface = 0;      // ablation: no near-surface updates
+		// The queue is drained one brick LATE: the entries it holds were queued -- and their colour and
+		// histogram sectors requested with prefetch.global.L2 -- while an earlier brick was evaluated, so
+		// the drain's dependent loads hit L2 instead of waiting for DRAM one after another.
+		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another brick: drain
+			nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
+			qcount = 0;
+		}
 		if (__any_sync(0xffffffffu, surface != 0)) {
 			if (surface) {
 				// surface-block map (Planes::occ): idempotent byte stores, no atomics.  A lane's VEC voxels
@@ -463,6 +657,13 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 					const int slot = qcount + __popc(m & ((1u << lane) - 1u));
 					const unsigned long long vv = (unsigned long long)(v0 + k);
 					q[slot] = make_uint4((unsigned)vv, (unsigned)(vv >> 32), (unsigned)img[k], (unsigned)w[k]);
+					if (!(f.debug & 16)) {
+						prefetch_l2(p.color + vv * 3);
+						if (LABELS) {
+							const unsigned label = __ldg(f.mask + img[k]);
+							if ((int)label < p.bins) prefetch_l2(p.hist + vv * (size_t)p.bins + label);
+						}
+					}
 				}
 				qcount += __popc(m);
 			}
@@ -483,16 +684,18 @@ __global__ void __launch_bounds__(256, 4) integrate_kernel(Planes p, VolGeom g, 
 			*reinterpret_cast<I *>(p.wt + v0) = wv;
 			if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 		}
-		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another brick: drain
-			nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
-			qcount = 0;
-		}
 	}
-	if (qcount) {
-		nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
-		qcount = 0;
-	}
-	}  // batch loop
+#if SFM_K1_PIPE
+	base = base_n; n = n_n; my_id = id_n;
+#else
+	base = __shfl_sync(0xffffffffu, next_raw, 0);
+	n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
+	my_id = lane < n ? list_at(base + lane) : 0u;
+	next_raw = fetch();
+	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+#endif
+	}  // fetch loop
+	if (qcount) nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
 
 	// fold U / S: warp shuffle, then one spread atomic pair per warp (no block barrier: warps with
 	// little work must not hold their slot waiting for the busiest warp of the block)

@@ -115,7 +115,9 @@ struct sfm_volume {
 	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
 	uint32_t *d_err = nullptr;
-	unsigned *d_work = nullptr;
+	unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
+	uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
+	size_t nbricks = 0;
 	int num_sms = 148;
 	size_t occ_bytes = 0;
 	uint8_t *d_palette = nullptr;
@@ -153,7 +155,7 @@ struct sfm_volume {
 	bool own_stream = false;
 	cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 	static constexpr int kRing = 2048;  // per-call event pairs around K1 (integrate kernel only)
-	cudaEvent_t ev_k0[kRing] = {}, ev_k1[kRing] = {};
+	cudaEvent_t ev_k0[kRing] = {}, ev_km[kRing] = {}, ev_k1[kRing] = {};  // before K1a | between | after K1b
 	uint64_t n_integrate = 0;
 	uint64_t launches = 0;
 	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
@@ -285,31 +287,62 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 	return f;
 }
 
-template <int VEC, bool LABELS, bool CULL, bool TMA_TILES>
-void launch_integrate3(sfm_volume *v, const FrameView &f, long long nbatches) {
-	// persistent grid: one resident wave (occupancy x SM count), never more blocks than batches need
-	// dynamic shared memory: the per-warp surface queues (+ the TMA-staged tile grids when enabled)
-	const size_t smem = 8 * kQueue * sizeof(uint4) + (TMA_TILES ? v->tile_bytes : 0);
-	static int per_sm = 0;
+// K1a: brick classification into the work lists
+template <int CPW, bool CULL, bool TMA_TILES>
+void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
+	// dynamic shared memory: [TMA-staged tile grids] [block-local MIXED list] [block-local FREE list]
+	const size_t smem = (TMA_TILES ? v->tile_bytes : 0) + 2 * (size_t)kSbPerBlock * 32 * sizeof(uint32_t);
+	auto kern = classify_kernel<CPW, CULL, TMA_TILES>;
 	static size_t smem_set = 0;
-	if (!per_sm || smem_set != smem) {
-		cudaFuncSetAttribute(integrate_kernel<VEC, LABELS, CULL, TMA_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrate_kernel<VEC, LABELS, CULL, TMA_TILES>, 256, smem) != cudaSuccess || per_sm < 1)
-			per_sm = 1;
+	if (smem > 48 * 1024 && smem_set != smem) {
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		smem_set = smem;
 	}
-	const long long want = (nbatches + 7) / 8;
+	// persistent-ish grid: 4 blocks per SM, more when a block would otherwise see > kSbPerBlock super-blocks
+	const long long want = (nsb + 7) / 8;
+	int blocks = (int)std::max<long long>(std::max(1LL, std::min<long long>(4LL * v->num_sms, want)), (nsb + kSbPerBlock - 1) / kSbPerBlock);
+	// without the TMA staging a block has no set-up cost: one super-block per warp, and the hardware
+	// block scheduler balances the (very uneven) super-block costs
+	if (!TMA_TILES || getenv("SFM_K1A_WIDE")) blocks = (int)std::max(1LL, want);
+	kern<<<blocks, 256, smem, v->stream>>>(v->g, f, wl);
+}
+
+template <int CPW>
+void launch_classify(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
+	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL), tma = !(v->desc.flags & SFM_FLAG_NO_TMA);
+	if (!cull) launch_classify2<CPW, false, false>(v, f, wl, nsb);
+	else if (tma) launch_classify2<CPW, true, true>(v, f, wl, nsb);
+	else launch_classify2<CPW, true, false>(v, f, wl, nsb);
+}
+
+// K1b: update of the listed bricks
+template <int VEC, bool LABELS, bool KCANON>
+void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
+	// persistent grid: one resident wave (occupancy x SM count); the warps pull bricks from the lists.
+	// dynamic shared memory: the per-warp surface queues
+	const size_t smem = 8 * kQueue * sizeof(uint4);
+	static int per_sm = 0;
+	auto kern = integrate_kernel<VEC, LABELS, KCANON>;
+	if (!per_sm) {
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1)
+			per_sm = 1;
+	}
+	const long long want = ((long long)v->nbricks + 7) / 8;
 	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));
-	integrate_kernel<VEC, LABELS, CULL, TMA_TILES><<<blocks, 256, smem, v->stream>>>(v->planes, v->g, f, v->d_stats, v->d_err, v->d_work);
+	kern<<<blocks, 256, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err);
 }
 
 template <int VEC, bool LABELS>
-void launch_integrate(sfm_volume *v, const FrameView &f, bool cull, long long nbatches) {
-	const bool tma = (v->desc.flags & SFM_FLAG_NO_TMA) == 0;
-	if (cull) {
-		if (tma) launch_integrate3<VEC, LABELS, true, true>(v, f, nbatches);
-		else launch_integrate3<VEC, LABELS, true, false>(v, f, nbatches);
-	} else launch_integrate3<VEC, LABELS, false, false>(v, f, nbatches);
+void launch_update(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
+	// pinhole pattern of K (see cam_to_screen): the only one the reference can build (tsdf.cu:137-150).
+	// The generic path stays for arbitrary K, for VEC = 1 and behind SFM_FLAG_GENERIC_K (A/B parity test).
+	const float *K = f.K;
+	bool canon = VEC == 4 && !(v->desc.flags & SFM_FLAG_GENERIC_K) && K[1] == 0.f && K[3] == 0.f && K[6] == 0.f &&
+		K[7] == 0.f && K[8] == 1.f;
+	for (int i = 0; i < 12 && canon; i++) canon = std::isfinite(f.E[i]) && fabsf(f.E[i]) < 1e15f;
+	if (VEC == 4 && canon) launch_update2<VEC, LABELS, VEC == 4>(v, f, wl);
+	else launch_update2<VEC, LABELS, false>(v, f, wl);
 }
 
 // K0 + K1 on device-resident frame images
@@ -321,27 +354,25 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	prep_frame_kernel<<<prep_blocks, 256, 0, v->stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
 		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err, v->d_work);
 	LAUNCH_CHECK(v);
-	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	const int cpw = vec4 ? 4 : 1;
-	const long long nbricks = (long long)v->g.Dx * ((v->g.Dy + cpw - 1) / cpw) * ((v->g.nz + 31) / 32);
-	const long long blocks = (nbricks + 31) / 32;  // number of 32-brick batches
-	{  // brick permutation multiplier ~ 0.618 * nbricks, coprime with nbricks
-		auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
-		long long m = (long long)(0.6180339887 * (double)nbricks) | 1;
-		while (m > 1 && gcd(m, nbricks) != 1) m -= 2;
-		// measured (round 1): the permutation balances the batches but costs image-cache locality and is
-		// 3 % slower overall, so it is opt-in
-		v->g.brick_mul = (getenv("SFM_PERMUTE_BRICKS") && m >= 1) ? m : 1;
-	}
+	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one 32-z chunk (k_integrate.cuh)
+	const long long rows = (v->g.Dy + cpw - 1) / cpw;
+	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + 31) / 32);
+	v->g.brick_mul = 1;
+	const WorkLists wl{v->d_list_mixed, v->d_list_free, v->d_work};
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
+	if (vec4) launch_classify<4>(v, f, wl, nsb);
+	else launch_classify<1>(v, f, wl, nsb);
+	LAUNCH_CHECK(v);
+	CU(cudaEventRecord(v->ev_km[slot], v->stream));
 	if (vec4) {
-		if (v->bins > 0) launch_integrate<4, true>(v, f, cull, blocks);
-		else launch_integrate<4, false>(v, f, cull, blocks);
+		if (v->bins > 0) launch_update<4, true>(v, f, wl);
+		else launch_update<4, false>(v, f, wl);
 	} else {
-		if (v->bins > 0) launch_integrate<1, true>(v, f, cull, blocks);
-		else launch_integrate<1, false>(v, f, cull, blocks);
+		if (v->bins > 0) launch_update<1, true>(v, f, wl);
+		else launch_update<1, false>(v, f, wl);
 	}
 	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_k1[slot], v->stream));
@@ -656,6 +687,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaEventCreate(&v->ev_t1));
 	for (int i = 0; i < sfm_volume::kRing; i++) {
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k0[i]));
+		CU_OR_DESTROY(cudaEventCreate(&v->ev_km[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k1[i]));
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
@@ -697,8 +729,19 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
-	CU_OR_DESTROY(cudaMalloc(&v->d_work, 4));
-	CU_OR_DESTROY(cudaMemset(v->d_work, 0, 4));
+	CU_OR_DESTROY(cudaMalloc(&v->d_work, 16));
+	CU_OR_DESTROY(cudaMemset(v->d_work, 0, 16));
+	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
+		const int cpw = (v->g.nz % 4 == 0) ? 4 : 1;
+		const size_t rows = ((size_t)v->g.Dy + cpw - 1) / cpw, chunks = ((size_t)v->g.nz + 31) / 32;
+		if (v->g.Dx > (1 << (32 - kIdXShift)) || rows > (1u << (kIdXShift - kIdGShift)) || chunks > (1u << kIdGShift)) {
+			sfm_destroy(v);
+			return fail(SFM_ERR_INVALID, "volume too large for the packed brick ids (x <= 2048, y <= 8192 (2048 when nz % 4 != 0), nz <= 32768)");
+		}
+		v->nbricks = (size_t)v->g.Dx * rows * chunks;
+		CU_OR_DESTROY(cudaMalloc(&v->d_list_mixed, v->nbricks * 4));
+		CU_OR_DESTROY(cudaMalloc(&v->d_list_free, v->nbricks * 4));
+	}
 	v->num_sms = prop.multiProcessorCount;
 	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 4));
 	CU_OR_DESTROY(cudaMalloc(&v->d_palette, 256 * 3));
@@ -740,7 +783,7 @@ void sfm_destroy(sfm_volume *v) {
 	for (int i = 0; i < sfm_volume::kStatRing; i++) if (v->ev_stat[i]) cudaEventDestroy(v->ev_stat[i]);
 	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
 	cudaFree(v->d_tilemax); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
-	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_palette); cudaFree(v->d_lut);
+	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_list_mixed); cudaFree(v->d_list_free); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);
 	for (int i = 0; i < 2; i++) {
@@ -754,6 +797,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->ev_t1) cudaEventDestroy(v->ev_t1);
 	for (int i = 0; i < sfm_volume::kRing; i++) {
 		if (v->ev_k0[i]) cudaEventDestroy(v->ev_k0[i]);
+		if (v->ev_km[i]) cudaEventDestroy(v->ev_km[i]);
 		if (v->ev_k1[i]) cudaEventDestroy(v->ev_k1[i]);
 	}
 	if (v->own_stream && v->stream) cudaStreamDestroy(v->stream);
@@ -1149,6 +1193,18 @@ int sfm_integrate_times(sfm_volume *v, float *ms, int n) {
 }
 
 int sfm_last_integrate_ms(sfm_volume *v, float *ms) { return sfm_integrate_times(v, ms, 1); }
+
+int sfm_integrate_times2(sfm_volume *v, float *ms_classify, float *ms_update, int n) {
+	if (!v || !ms_classify || !ms_update || n < 0) return fail(SFM_ERR_INVALID, "bad argument");
+	if ((uint64_t)n > v->n_integrate || n > sfm_volume::kRing) return fail(SFM_ERR_INVALID, "fewer integrate calls recorded than requested");
+	for (int i = 0; i < n; i++) {
+		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
+		CU(cudaEventSynchronize(v->ev_k1[slot]));
+		CU(cudaEventElapsedTime(ms_classify + i, v->ev_k0[slot], v->ev_km[slot]));
+		CU(cudaEventElapsedTime(ms_update + i, v->ev_km[slot], v->ev_k1[slot]));
+	}
+	return SFM_OK;
+}
 
 /* U = voxels whose weight was incremented, S = voxels whose colour/histogram was updated, summed
  * over the integrate calls since the previous sfm_frame_stats call. */

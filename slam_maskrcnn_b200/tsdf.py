@@ -245,6 +245,12 @@ class Volume:
         check(self.lib.sfm_integrate_times(self._h, _ptr(ms), n))
         return ms
 
+    def integrate_times2(self, n):
+        """(K1a classification ms, K1b update ms) of the last n integrate calls."""
+        a, b = np.empty(n, np.float32), np.empty(n, np.float32)
+        check(self.lib.sfm_integrate_times2(self._h, _ptr(a), _ptr(b), n))
+        return a, b
+
     def stats_begin(self):
         t = C.c_uint64()
         check(self.lib.sfm_stats_begin(self._h, C.byref(t)))
