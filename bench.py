@@ -268,15 +268,20 @@ def run_ours(args):
     n_pool = min(args.pool, K_steps + W_steps)
     sc, K, Kinv, place, frames = make_frames(n_pool, dims, args.hole_model)
     # z-slab plan: equal thickness is badly balanced under brick culling (the near planes carry the
-    # free-space updates, the planes behind the surfaces nothing), so the slab boundaries follow a
-    # work profile measured on the GPU from the first frames (coarse 128^3 pre-pass, labels off)
+    # free-space updates, the planes behind the surfaces nothing, the ~10 planes of a fronto-parallel wall
+    # all of its colour/histogram updates), so the slab boundaries follow a per-plane cost profile measured
+    # on the GPU from the first frames at full z resolution (128 x 128 x Dz pre-pass, one histogram bin)
     from slam_maskrcnn_b200 import slabs as slabs_mod
+    profile = None
     if world > 1 and not args.equal_slabs:
-        def coarse_volume(cdims):
-            cv = Volume(dims=cdims, bins=0, width=640, height=480, K=K, Kinv=Kinv, device=local)
-            cv.set_bounds(place[0], place[1])
-            return cv
-        profile = slabs_mod.work_profile(coarse_volume, frames[:3], dims[2])
+        def profile_volume(pdims):
+            pv = Volume(dims=pdims, bins=1, width=640, height=480, K=K, Kinv=Kinv, device=local)
+            s_, e_ = np.asarray(place[0], np.float32), np.asarray(place[1], np.float32)
+            vox = (e_ - s_) / (np.array(pdims, np.float32) - np.float32(1))
+            vox[2] = np.float32(place[2][2])  # the fine volume's z voxel and truncation distance
+            pv.set_bounds(s_, e_, vox, place[3])
+            return pv
+        profile, _, _ = slabs_mod.work_profile_z(profile_volume, frames[:3], dims)
         plan = slabs_mod.plan_slabs(dims[2], world, profile)
     else:
         plan = slabs_mod.plan_slabs(dims[2], world)
@@ -288,10 +293,9 @@ def run_ours(args):
         return v
 
     vol = make_volume(plan)
-    # calibration (N > 1): the U-based profile misses what makes planes near the surfaces expensive
-    # (partially touched bricks, colour/histogram updates), so the plan is refined from measured
-    # per-rank kernel times: a few frames are integrated, the cost density of every old slab becomes
-    # time/planes, the slabs are re-planned and the volume re-allocated.  Part of set-up, not timed.
+    # calibration (N > 1): the profile's cost model is approximate, so the plan is refined from measured
+    # per-rank kernel times: a few frames are integrated, the profile inside every slab is rescaled to the
+    # slab's measured time, the slabs are re-planned and the volume re-allocated.  Part of set-up, not timed.
     calib = []
     if world > 1 and not args.equal_slabs:
         for it in range(args.calibrate):
@@ -304,8 +308,8 @@ def run_ours(args):
             dist.all_gather(ts, torch.tensor([t_mine], dtype=torch.float64, device="cuda"))
             ts = [float(t.item()) for t in ts]
             calib.append([round(t, 4) for t in ts])
-            prof = np.concatenate([np.full(n, t / n) for (z0, n), t in zip(plan, ts)])
-            new_plan = slabs_mod.plan_slabs(dims[2], world, prof / prof.sum())
+            profile = slabs_mod.refine_profile(profile, plan, ts)
+            new_plan = slabs_mod.plan_slabs(dims[2], world, profile)
             if new_plan == plan:
                 break
             plan = new_plan
@@ -428,7 +432,9 @@ def run_ours(args):
     t_dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = vol.launch_count() - launches0
     U, S = vol.frame_stats()
+    # K1 = K1a (classification into brick lists) + K1b (update of the listed bricks, the dominant kernel)
     k1_ms = vol.integrate_times(min(K_steps, 2048)).astype(np.float64)
+    k1a_ms, k1b_ms = (t.astype(np.float64) for t in vol.integrate_times2(min(K_steps, 2048)))
     k1_ms_max = max_over_ranks(float(k1_ms.mean()))
     per_rank = None
     if world > 1:
@@ -502,10 +508,11 @@ def run_ours(args):
     alg_bytes = 16.0 * U + 14.0 * S + (FRAME_BYTES + POSE_BYTES) * K_steps
     alg_per_launch = alg_bytes / K_steps
     peak, peak_src = measured_peaks()
-    achieved = alg_per_launch / (k1_ms.mean() * 1e-3) / 1e9
+    achieved = alg_per_launch / (k1b_ms.mean() * 1e-3) / 1e9
+    achieved_step = alg_per_launch / (k1_ms.mean() * 1e-3) / 1e9
     # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1b_k1_traffic.json")
     if world == 1 and tuple(dims) == (512, 512, 512) and bins == 80 and args.hole_model == "tum" and os.path.exists(tpath):
         with open(tpath) as tf:
             traffic = json.load(tf)["dram_bytes_per_launch"]
@@ -532,7 +539,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, dims), "dims": list(dims), "bins": bins,
                        "voxels_per_gpu": n_vox_total // world, "z_slabs": [list(p) for p in plan],
-                       "slab_plan": "equal thickness" if (world == 1 or args.equal_slabs) else "boundaries from a GPU work profile of the first 3 frames (coarse 128^3 pre-pass), refined from measured per-rank kernel times in an untimed calibration pass; slabs <= 3x the mean thickness",
+                       "slab_plan": "equal thickness" if (world == 1 or args.equal_slabs) else "boundaries from a per-plane GPU cost profile of the first 3 frames (128x128xDz pre-pass: touched and near-surface voxels per plane), rescaled per slab from measured kernel times in an untimed calibration pass; slabs <= 3x the mean thickness",
                        "slab_calibration_ms": calib,
                        "frame_pool": n_pool,
                        "invalid_depth_model": args.hole_model + (" (15 % invalid pixels, spatially clustered like the TUM fr2 frames the reference ships)"
@@ -542,8 +549,11 @@ def run_ours(args):
             "touched_voxel_updates_per_s": U_all / (t_dev_ms * 1e-3),
             "U_per_step": U_all / K_steps, "S_per_step": S_all / K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "profiles/r1_k1_traffic.json (ncu --set full, per launch)" if traffic else None, "peak_source": peak_src, "kernel": "integrate_kernel<4,true,true> (K1)",
-                         "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_avg": float(k1_ms.mean()),
+                         "traffic": traffic, "traffic_source": "profiles/r1b_k1_traffic.json (ncu --set full, per launch)" if traffic else None, "peak_source": peak_src,
+                         "kernel": "integrate_kernel<4,true,true> (K1b: update of the bricks listed by K1a classify_kernel)",
+                         "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_avg": float(k1b_ms.mean()),
+                         "classify_kernel_ms_avg": float(k1a_ms.mean()), "integrate_step_ms_avg": float(k1_ms.mean()),
+                         "frac_incl_classify_kernel": achieved_step / peak,
                          "kernel_ms_avg_max_rank": k1_ms_max, "launches_timed": n_timed,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "voxel-updates/s", "h2d_bytes_per_step": FRAME_BYTES,

@@ -353,11 +353,14 @@ constexpr int kSbPerBlock = 64;                // most super-blocks one K1a bloc
 // one brick.  Surviving bricks are appended to the MIXED / FREE lists with one atomic per warp and
 // list.  The tile grids are staged into shared memory once per block by a TMA bulk copy.
 // ---------------------------------------------------------------------------------------------
-template <int CPW, bool CULL, bool TMA_TILES>
+template <bool VEC4, bool CULL, bool TMA_TILES>
 __global__ void __launch_bounds__(256) classify_kernel(VolGeom g, FrameView f, WorkLists wl)
 {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int nchunks = (g.nz + 31) >> 5;
+	const int zsh = VEC4 ? g.zl_log2 : 5;   // log2 lanes along z per column
+	const int CPW = 32 >> zsh;              // columns per brick
+	const int csh = zsh + (VEC4 ? 2 : 0);   // log2 planes per z chunk
+	const int lane = threadIdx.x & 31;
+	const int nchunks = (g.nz + (1 << csh) - 1) >> csh;
 	const int groups_per_x = (g.Dy + CPW - 1) / CPW;
 	const int nsby = (groups_per_x + kSbG - 1) / kSbG;
 	const unsigned nsb = (unsigned)((g.Dx + kSbX - 1) / kSbX) * (unsigned)nsby * (unsigned)nchunks;
@@ -394,14 +397,25 @@ __global__ void __launch_bounds__(256) classify_kernel(VolGeom g, FrameView f, W
 	__shared__ unsigned s_cnt[2], s_base[2];
 	uint32_t *s_mixed = reinterpret_cast<uint32_t *>(smem_dyn + (TMA_TILES ? f.tile_bytes : 0));
 	uint32_t *s_free = s_mixed + kSbPerBlock * 32;
+	// The block owns the super-blocks blockIdx.x + k * gridDim.x (a sample of the whole volume, so every
+	// block gets about the same mix of culled and surviving boxes); its warps pull k from a shared
+	// counter, so a warp that lands on culled boxes takes more of them.
+	__shared__ unsigned s_next;
 	if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+	if (threadIdx.x == 2) s_next = 0;
 	__syncthreads();
-	for (unsigned sb = blockIdx.x * 8u + warp; sb < nsb; sb += gridDim.x * 8u) {
+	for (;;) {
+		unsigned k = 0;
+		if (lane == 0) k = atomicAdd(&s_next, 1u);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		const unsigned long long sb64 = (unsigned long long)blockIdx.x + (unsigned long long)k * gridDim.x;
+		if (sb64 >= nsb) break;
+		const unsigned sb = (unsigned)sb64;
 		// super-block -> box (z chunk fastest)
 		const int sbz = (int)(sb % (unsigned)nchunks);
 		const unsigned sbt = sb / (unsigned)nchunks;
 		const int gy0 = (int)(sbt % (unsigned)nsby) * kSbG, x0 = (int)(sbt / (unsigned)nsby) * kSbX;
-		const int zc0 = sbz << 5, zc1 = min(zc0 + 31, g.nz - 1);
+		const int zc0 = sbz << csh, zc1 = min(zc0 + (1 << csh) - 1, g.nz - 1);
 		int sbcls = kMixed;
 		if (CULL && !(f.debug & 8))
 			sbcls = classify_superblock(f, g, s_tilemax, s_tilemin, x0, min(x0 + kSbX - 1, g.Dx - 1), gy0 * CPW,
@@ -441,12 +455,13 @@ template <int VEC, bool LABELS, bool KCANON>
 __global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
 	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
 {
-	constexpr int LPC = 32 / VEC;  // lanes per column
-	constexpr int CPW = 32 / LPC;  // columns per brick
+	const int zsh = VEC == 4 ? g.zl_log2 : 5;  // log2 lanes along z per column (3: a brick is 4 columns x 32 planes)
+	const int CPW = 32 >> zsh;                 // columns per brick
+	const int csh = zsh + (VEC == 4 ? 2 : 0);  // log2 planes per z chunk
 	using F = typename VecT<VEC>::F;
 	using I = typename VecT<VEC>::I;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int zq = lane % LPC, ci = lane / LPC;
+	const int zq = lane & ((1 << zsh) - 1), ci = lane >> zsh;
 	unsigned nU = 0, nS = 0;
 	// dynamic shared memory: 8 warps x kQueue deferred near-surface voxels {voxel lo, hi, pixel, weight}
 	extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Plane
 	auto brick_coords = [&](unsigned id, int &x, int &y, int &zl) {  // warp-uniform id + lane offsets
 		x = (int)(id >> kIdXShift);
 		y = (int)((id >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW + ci;
-		zl = (int)((id & ((1u << kIdGShift) - 1u)) << 5) + zq * VEC;
+		zl = (int)((id & ((1u << kIdGShift) - 1u)) << csh) + zq * VEC;
 	};
 	auto brick_voxel = [&](int x, int y, int zl, bool ok) { return ((size_t)x * g.Dy + (ok ? y : 0)) * (size_t)g.nz + (ok ? zl : 0); };
 	// Software pipeline: the SDF / weight quads of brick i+1 are requested before brick i is
@@ -494,11 +509,30 @@ __global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Plane
 		if (lane == 0) b = atomicAdd(wl.counts + 2, (unsigned)kFetch);
 		return b;
 	};
+	// prefetch.global.L2 of the SDF / weight lines of bricks 1.. of a freshly fetched group (brick 0 is
+	// requested into registers right away): by the time the 128-bit loads ask for them they sit in L2
+	auto prefetch_group = [&](unsigned ids, int cnt) {
+		// the lanes that start a column segment (zq == 0) request its SDF and weight lines
+#pragma unroll
+		for (int bi = 1; bi < kFetch; bi++) {
+			const unsigned id = __shfl_sync(0xffffffffu, ids, bi);
+			if (bi < cnt && zq == 0 && !(f.debug & 32)) {
+				int x, y, zl;
+				brick_coords(id, x, y, zl);
+				if (y < g.Dy) {
+					const size_t v = ((size_t)x * g.Dy + y) * (size_t)g.nz + zl;
+					prefetch_l2(p.sdf + v);
+					prefetch_l2(p.wt + v);
+				}
+			}
+		}
+	};
 	unsigned base = __shfl_sync(0xffffffffu, fetch(), 0);
 	int n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
 	unsigned my_id = lane < n ? list_at(base + lane) : 0u;
 	unsigned next_raw = fetch();
 	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+	if (n > 1) prefetch_group(my_id, n);
 	while (n > 0) {
 #if SFM_K1_PIPE
 	// ids of the next group: requested now, needed when the last brick of this group prefetches
@@ -693,6 +727,7 @@ __global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Plane
 	my_id = lane < n ? list_at(base + lane) : 0u;
 	next_raw = fetch();
 	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+	if (n > 1) prefetch_group(my_id, n);
 #endif
 	}  // fetch loop
 	if (qcount) nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);

@@ -288,11 +288,11 @@ FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *
 }
 
 // K1a: brick classification into the work lists
-template <int CPW, bool CULL, bool TMA_TILES>
+template <bool VEC4, bool CULL, bool TMA_TILES>
 void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
 	// dynamic shared memory: [TMA-staged tile grids] [block-local MIXED list] [block-local FREE list]
 	const size_t smem = (TMA_TILES ? v->tile_bytes : 0) + 2 * (size_t)kSbPerBlock * 32 * sizeof(uint32_t);
-	auto kern = classify_kernel<CPW, CULL, TMA_TILES>;
+	auto kern = classify_kernel<VEC4, CULL, TMA_TILES>;
 	static size_t smem_set = 0;
 	if (smem > 48 * 1024 && smem_set != smem) {
 		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -307,12 +307,12 @@ void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, lo
 	kern<<<blocks, 256, smem, v->stream>>>(v->g, f, wl);
 }
 
-template <int CPW>
+template <bool VEC4>
 void launch_classify(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
 	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL), tma = !(v->desc.flags & SFM_FLAG_NO_TMA);
-	if (!cull) launch_classify2<CPW, false, false>(v, f, wl, nsb);
-	else if (tma) launch_classify2<CPW, true, true>(v, f, wl, nsb);
-	else launch_classify2<CPW, true, false>(v, f, wl, nsb);
+	if (!cull) launch_classify2<VEC4, false, false>(v, f, wl, nsb);
+	else if (tma) launch_classify2<VEC4, true, true>(v, f, wl, nsb);
+	else launch_classify2<VEC4, true, false>(v, f, wl, nsb);
 }
 
 // K1b: update of the listed bricks
@@ -355,16 +355,16 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err, v->d_work);
 	LAUNCH_CHECK(v);
 	const bool vec4 = (v->g.nz % 4 == 0);
-	const int cpw = vec4 ? 4 : 1;
-	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one 32-z chunk (k_integrate.cuh)
+	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one z chunk (k_integrate.cuh)
+	const int cpw = vec4 ? (32 >> v->g.zl_log2) : 1, chunk = vec4 ? (4 << v->g.zl_log2) : 32;
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
-	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + 31) / 32);
+	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
 	v->g.brick_mul = 1;
 	const WorkLists wl{v->d_list_mixed, v->d_list_free, v->d_work};
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
-	if (vec4) launch_classify<4>(v, f, wl, nsb);
-	else launch_classify<1>(v, f, wl, nsb);
+	if (vec4) launch_classify<true>(v, f, wl, nsb);
+	else launch_classify<false>(v, f, wl, nsb);
 	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_km[slot], v->stream));
 	if (vec4) {
@@ -732,8 +732,25 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->d_work, 16));
 	CU_OR_DESTROY(cudaMemset(v->d_work, 0, 16));
 	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
-		const int cpw = (v->g.nz % 4 == 0) ? 4 : 1;
-		const size_t rows = ((size_t)v->g.Dy + cpw - 1) / cpw, chunks = ((size_t)v->g.nz + 31) / 32;
+		// brick shape on the 128-bit path: 32 planes per brick unless the slab is so thin that more than half the lanes
+		// of such a brick would fall outside it (see VolGeom::zl_log2); SFM_ZL_LOG2 overrides (experiments)
+		const bool vec4 = v->g.nz % 4 == 0;
+		int zl = 3;
+		if (vec4) {
+			double best = 0.0;
+			for (int c = 3; c >= 0; c--) {
+				const int planes = 4 << c;
+				best = std::max(best, (double)v->g.nz / (double)(((v->g.nz + planes - 1) / planes) * planes));
+			}
+			for (int c = 3; c >= 0; c--) {
+				const int planes = 4 << c;
+				if ((double)v->g.nz / (double)(((v->g.nz + planes - 1) / planes) * planes) >= 0.5 * best) { zl = c; break; }
+			}
+			if (const char *e = getenv("SFM_ZL_LOG2")) zl = std::min(3, std::max(0, atoi(e)));
+		}
+		v->g.zl_log2 = zl;
+		const int cpw = vec4 ? (32 >> zl) : 1, planes = vec4 ? (4 << zl) : 32;
+		const size_t rows = ((size_t)v->g.Dy + cpw - 1) / cpw, chunks = ((size_t)v->g.nz + planes - 1) / planes;
 		if (v->g.Dx > (1 << (32 - kIdXShift)) || rows > (1u << (kIdXShift - kIdGShift)) || chunks > (1u << kIdGShift)) {
 			sfm_destroy(v);
 			return fail(SFM_ERR_INVALID, "volume too large for the packed brick ids (x <= 2048, y <= 8192 (2048 when nz % 4 != 0), nz <= 32768)");

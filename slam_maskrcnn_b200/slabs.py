@@ -47,6 +47,36 @@ def work_profile(volume_factory, frames, dz, coarse=128, fixed_share=0.2):
     return prof / prof.sum()
 
 
+# Relative cost of K1 per voxel of each kind, measured on B200 (profiles/README.md): a voxel that only
+# gets its weight bumped (free space), a near-surface voxel (colour + histogram read-modify-write: bound
+# by random 32-byte DRAM sector traffic when a rank owns little else), and the classification every voxel
+# of a plane pays whether it is touched or not.
+COST_FREE, COST_SURFACE, COST_VISIT = 1.0, 11.0, 0.03
+
+
+def work_profile_z(volume_factory, frames, dims, coarse_xy=128):
+    """Per-plane integration cost at FULL z resolution, estimated on the GPU.  The truncation band is
+    5 voxels of the fine volume thick, so a fronto-parallel wall concentrates all its colour/histogram
+    updates in ~10 fine planes: a profile taken on a coarser z grid smears exactly the feature the slab
+    plan has to resolve.  `volume_factory((cx, cy, dz))` must return a placed Volume with bins = 1 whose
+    x/y voxels are coarser but whose z voxel size and truncation distance are the fine volume's.  The
+    frames are integrated with an all-zero label image: the weight plane then counts the touched voxels
+    per plane (U) and histogram bin 0 the near-surface voxels (S)."""
+    dx, dy, dz = dims
+    cx, cy = min(coarse_xy, dx), min(coarse_xy, dy)
+    vol = volume_factory((cx, cy, dz))
+    zero = np.zeros_like(frames[0]["gt"])
+    for fr in frames:
+        vol.integrate_raw(fr["depth"], fr["color"], zero, fr["extrinsic"])
+    u = vol.download("weight").astype(np.float64).sum(axis=(0, 1))
+    s_ = vol.download("hist").astype(np.float64).sum(axis=(0, 1, 3))
+    vol.close()
+    scale = (dx * dy) / float(cx * cy) / max(len(frames), 1)
+    u, s_ = u * scale, s_ * scale
+    cost = COST_FREE * (u - s_) + COST_SURFACE * s_ + COST_VISIT * dx * dy
+    return cost / cost.sum(), u, s_
+
+
 def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
     """Contiguous z-slabs [(z0, nz)] for `world` ranks.  Without a profile: equal thickness.  With a
     per-plane cost profile: the partition minimising the largest slab cost subject to every slab being
@@ -66,8 +96,9 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
         for r in range(world):
             acc, n = 0.0, 0
             remaining_slabs = world - r - 1
-            while i < nchunks and n < max_c and nchunks - i > remaining_slabs:  # leave >= 1 chunk per later slab
-                if n > 0 and acc + cost[i] > bound:
+            # leave >= 1 chunk per later slab, and no more than the later slabs can hold
+            while i < nchunks and n < max_c and nchunks - i > remaining_slabs:
+                if n > 0 and acc + cost[i] > bound and (nchunks - i) <= remaining_slabs * max_c:
                     break
                 acc += cost[i]
                 i += 1
@@ -75,16 +106,32 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
             cuts.append(i)
         return cuts if i == nchunks else None
 
+    def worst(cuts):
+        return max(cost[cuts[r]:cuts[r + 1]].sum() for r in range(world))
+
     lo, hi = 1.0 / world, 1.0
     best = sweep(hi)
-    for _ in range(40):
+    for _ in range(50):
         mid = 0.5 * (lo + hi)
         c = sweep(mid)
-        if c is not None:
+        if c is not None and worst(c) <= mid + 1e-12:
             best, hi = c, mid
         else:
             lo = mid
     return [(best[r] * align, (best[r + 1] - best[r]) * align) for r in range(world)]
+
+
+def refine_profile(profile, plan, measured_ms):
+    """Calibration step: rescale the per-plane profile inside every slab so that the slab's share of the
+    profile equals its share of the measured kernel time (the SHAPE inside a slab is kept -- a flat
+    per-slab density would smear a wall that sits at one end of a slab)."""
+    prof = np.asarray(profile, np.float64).copy()
+    t = np.asarray(measured_ms, np.float64)
+    for (z0, n), ti in zip(plan, t):
+        seg = prof[z0:z0 + n]
+        tot = seg.sum()
+        prof[z0:z0 + n] = (seg / tot if tot > 0 else np.full(n, 1.0 / n)) * ti
+    return prof / prof.sum()
 
 
 def frame_nbytes(width=FRAME_W, height=FRAME_H):

@@ -145,3 +145,40 @@ def test_tma_staged_tile_grids_are_exact():
     b, sb = run_ours(sc, flags=FLAG_NO_TMA)
     assert_planes_equal(a, b, "TMA tiles vs L1 tiles")
     assert sa == sb
+
+
+def test_pinhole_k_fast_path_is_exact():
+    """K*c with the exact-zero terms dropped (default for a pinhole K) vs all nine terms (SFM_FLAG_GENERIC_K)."""
+    from slam_maskrcnn_b200 import FLAG_GENERIC_K
+    sc = Scenario(dims=(96, 96, 96), bins=16, frames=4, yaw_step_deg=4.0)
+    a, sa = run_ours(sc, flags=0)
+    b, sb = run_ours(sc, flags=FLAG_GENERIC_K)
+    assert_planes_equal(a, b, "pinhole-K fast path vs generic K")
+    assert sa == sb
+
+
+@pytest.mark.parametrize("zl", [0, 1, 2, 3])
+def test_brick_shapes_are_exact(zl, monkeypatch):
+    """K1's brick shape ((32 >> zl) columns x (4 << zl) planes; thin z-slabs use flat bricks) never changes a bit."""
+    sc = Scenario(dims=(64, 72, 64), bins=16, frames=4, yaw_step_deg=3.0)
+    orc, ostats = run_cpu_oracle(sc)
+    monkeypatch.setenv("SFM_ZL_LOG2", str(zl))
+    ours, stats = run_ours(sc)
+    assert_planes_equal(ours, orc, f"zl_log2={zl} vs CPU oracle")
+    assert stats == ostats
+
+
+@pytest.mark.parametrize("slab", [(20, 8), (12, 12), (8, 40), (0, 4), (28, 36)])
+def test_thin_slabs_hold_identical_planes(slab):
+    """A handle that stores only planes [z0, z0+nz) -- down to 4 planes, the brick shape follows nz -- holds
+    the same bits as those planes of the whole volume."""
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=4, yaw_step_deg=3.0)
+    full, _ = run_ours(sc)
+    z0, nz = slab
+    v = sc.make_volume(slab=slab)
+    for fr in sc.frames:
+        v.integrate_raw(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"])
+    part = {k: v.download(k) for k in ("sdf", "weight", "color", "hist")}
+    v.close()
+    assert_planes_equal(part, {k: full[k][:, :, z0:z0 + nz] for k in part}, f"slab {slab} vs whole volume")
+    assert part["weight"].sum() > 0
