@@ -183,6 +183,26 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
 	const void *d_ev1, const void *d_ev2, void *d_out);
 int sfm_shard_halo(const float *voxel3);
+/* Duplicate-instance merge over z-slabs (tsdf.cu:426-461 on a sharded volume).  Per frame and rank:
+ *   1. sfm_shard_backproj_stage(v, 1|2|3, extrinsic2init, ...) -- the three stages of the exact sharded march
+ *      (see sfm_shard_raycast_stage) from the INCOMING camera; the caller MIN-all-reduces each stage's
+ *      output.  Stage 3 also keeps the hit positions this rank owns inside the handle.
+ *   2. sfm_shard_fold(v, d_mask, d_keys_global, do_counts, d_tables) -- folds the owned hits into the
+ *      overlap tables (fixed-point integers, sfm_fold_table_bytes() gives the size and the length of the
+ *      leading int64 part; the rest is int32); exactly one rank passes do_counts = 1.  The caller
+ *      SUM-all-reduces d_tables (int64 part and int32 part): integer sums are exact and order-independent,
+ *      so the result equals the single-GPU tables bit for bit.
+ *   3. sfm_shard_merge_finish(v, d_tables_reduced, d_mask_inout, lut256, report) -- the decision half of
+ *      filter_overlaps (tsdf.cu:335-389) on every rank (same inputs, same result), relabels the device mask
+ *      in place and returns the 256-entry label map for the caller's host copy.
+ *   4. sfm_integrate_dev(v, d_depth, d_color, d_mask_inout, extrinsic2init).
+ * All device pointers are caller-owned; the mask is u8[H*W]. */
+int sfm_shard_backproj_stage(sfm_volume *v, int stage, const float *extrinsic2init16, const void *d_ev1, const void *d_ev2, void *d_out);
+int sfm_shard_first_frame(sfm_volume *v, const void *d_mask);  /* n_obs == 0: num_objs = max(mask)+1, tsdf.cu:464-467 */
+int sfm_fold_table_bytes(int bins, size_t *bytes_i64, size_t *bytes_total);
+int sfm_shard_fold(sfm_volume *v, const void *d_mask, const void *d_keys_global, int do_counts, void *d_tables);
+int sfm_shard_merge_finish(sfm_volume *v, const void *d_tables_reduced, void *d_mask_inout, uint8_t *lut256, sfm_merge_report *report);
+
 /* key image (device) -> BGR image (host) through the palette (viewer.cu:80-83). */
 int sfm_keys_to_bgr(sfm_volume *v, const void *d_keys, int w, int h, uint8_t *bgr);
 /* Viewer::show_tsdf (viewer.cu:137-179): orbit camera matrices + ray-cast. */

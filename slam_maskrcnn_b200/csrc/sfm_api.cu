@@ -476,21 +476,50 @@ FoldLayout fold_layout(int L) {
 	return f;
 }
 
-// launch the fused back-project + fold on the device mask; tables end up in v->h_fold (pinned)
-int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
+__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut);
+void combine_tables(const sfm_volume *v, int max_obj_now, double *A, uint32_t *C);
+void decide(const sfm_volume *v, const double *A, const uint32_t *C, int max_obj_now, const unsigned *first_pix,
+	int *num_objs, sfm_merge_report *rep);
+
+FoldTables fold_tables_at(uint8_t *base, int L) {
+	const FoldLayout fl = fold_layout(L);
+	FoldTables tb;
+	tb.Pos = (long long *)(base + fl.oPos);
+	tb.Tm = (long long *)(base + fl.oTm);
+	tb.T = (long long *)(base + fl.oT);
+	tb.Bm = (unsigned *)(base + fl.oBm);
+	tb.B = (unsigned *)(base + fl.oB);
+	tb.Cm = (unsigned *)(base + fl.oCm);
+	tb.NoHit = (unsigned *)(base + fl.oNoHit);
+	tb.FirstPix = (unsigned *)(base + fl.oFirst);
+	return tb;
+}
+
+// zero the tables at `d_tables` and fold the hits in v->d_hits into them (see fold_kernel)
+int launch_fold(sfm_volume *v, uint8_t *d_tables, const uint8_t *d_mask, const unsigned long long *d_gkeys, int do_counts) {
 	const int L = v->bins;
 	const FoldLayout fl = fold_layout(L);
-	CU(cudaMemsetAsync(v->d_fold, 0, fl.oFirst, v->stream));
-	CU(cudaMemsetAsync(v->d_fold + fl.oFirst, 0xff, (size_t)L * 4, v->stream));
-	FoldTables tb;
-	tb.Pos = (long long *)(v->d_fold + fl.oPos);
-	tb.Tm = (long long *)(v->d_fold + fl.oTm);
-	tb.T = (long long *)(v->d_fold + fl.oT);
-	tb.Bm = (unsigned *)(v->d_fold + fl.oBm);
-	tb.B = (unsigned *)(v->d_fold + fl.oB);
-	tb.Cm = (unsigned *)(v->d_fold + fl.oCm);
-	tb.NoHit = (unsigned *)(v->d_fold + fl.oNoHit);
-	tb.FirstPix = (unsigned *)(v->d_fold + fl.oFirst);
+	CU(cudaMemsetAsync(d_tables, 0, fl.total, v->stream));
+	if (do_counts) CU(cudaMemsetAsync(d_tables + fl.oFirst, 0xff, (size_t)L * 4, v->stream));
+	const FoldTables tb = fold_tables_at(d_tables, L);
+	const RayVol V = make_ray_vol(v);
+	const int npix = v->W * v->H;
+	const int blocks = (npix + 127) / 128;
+	const float n_obs = (float)v->n_obs, prior = v->desc.prior_err_rate, pres = v->desc.presence_thresh;
+	const int nb = (L + 31) / 32;
+	switch (nb) {
+	case 1: fold_kernel<1><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb, d_gkeys, do_counts); break;
+	case 2: fold_kernel<2><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb, d_gkeys, do_counts); break;
+	case 3: fold_kernel<3><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb, d_gkeys, do_counts); break;
+	case 4: fold_kernel<4><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb, d_gkeys, do_counts); break;
+	default: fold_kernel<8><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb, d_gkeys, do_counts); break;
+	}
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+// launch the fused back-project + fold on the device mask; tables end up in v->h_fold (pinned)
+int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	const RayVol V = make_ray_vol(v);
 	const RayCam cam = make_backproj_cam(v, E16);
 	const int npix = v->W * v->H;
@@ -498,19 +527,34 @@ int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	if (rc) return rc;
 	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr);
 	LAUNCH_CHECK(v);
-	const int blocks = (npix + 127) / 128;
-	const float n_obs = (float)v->n_obs, prior = v->desc.prior_err_rate, pres = v->desc.presence_thresh;
-	const int nb = (L + 31) / 32;
-	switch (nb) {
-	case 1: fold_kernel<1><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
-	case 2: fold_kernel<2><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
-	case 3: fold_kernel<3><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
-	case 4: fold_kernel<4><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
-	default: fold_kernel<8><<<blocks, 128, 0, v->stream>>>(V, npix, v->d_hits, d_mask, n_obs, prior, pres, tb); break;
-	}
-	LAUNCH_CHECK(v);
-	CU(cudaMemcpyAsync(v->h_fold, v->d_fold, fl.total, cudaMemcpyDeviceToHost, v->stream));
+	rc = launch_fold(v, v->d_fold, d_mask, nullptr, 1);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(v->h_fold, v->d_fold, fold_layout(v->bins).total, cudaMemcpyDeviceToHost, v->stream));
 	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+// tables in v->h_fold -> decision -> relabel of the device mask; lut_out[256] (optional) gets the map
+int decide_and_relabel(sfm_volume *v, int mx, uint8_t *d_mask, uint8_t *lut_out) {
+	const int L = v->bins;
+	const size_t npx = (size_t)v->W * v->H;
+	std::vector<double> A((size_t)L * L);
+	std::vector<uint32_t> C((size_t)L * L);
+	combine_tables(v, mx + 1, A.data(), C.data());
+	const unsigned *first = (const unsigned *)(v->h_fold + fold_layout(L).oFirst);
+	sfm_merge_report rep;
+	decide(v, A.data(), C.data(), mx + 1, first, &v->num_objs, &rep);
+	v->last_merge = rep;
+	int newmax = 0;
+	uint8_t lut[256];
+	for (int m = 0; m < 256; m++) { lut[m] = (uint8_t)rep.assign[m]; if (m <= mx) newmax = std::max(newmax, rep.assign[m]); }
+	if (newmax >= L)
+		return fail(SFM_ERR_INVALID, "merge produced a global instance id >= bins (num_objs outgrew the histogram; the reference overflows here, tsdf.cu:61,383)");
+	// relabel on the device (LUT); the copy is from pageable memory: the runtime stages it before returning
+	CU(cudaMemcpyAsync(v->d_lut, lut, 256, cudaMemcpyHostToDevice, v->stream));
+	relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(d_mask, (int)npx, v->d_lut);
+	LAUNCH_CHECK(v);
+	if (lut_out) memcpy(lut_out, lut, 256);
 	return SFM_OK;
 }
 
@@ -951,26 +995,11 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 			if (rc) return rc;
 			rc = run_fold(v, E16, v->d_mask);
 			if (rc) return rc;
-			const int L = v->bins;
-			std::vector<double> A((size_t)L * L);
-			std::vector<uint32_t> C((size_t)L * L);
-			combine_tables(v, mx + 1, A.data(), C.data());
-			const unsigned *first = (const unsigned *)(v->h_fold + fold_layout(L).oFirst);
-			sfm_merge_report rep;
-			decide(v, A.data(), C.data(), mx + 1, first, &v->num_objs, &rep);
-			v->last_merge = rep;
-			int newmax = 0;
 			uint8_t lut[256];
-			for (int m = 0; m < 256; m++) { lut[m] = (uint8_t)rep.assign[m]; if (m <= mx) newmax = std::max(newmax, rep.assign[m]); }
-			if (newmax >= L)
-				return fail(SFM_ERR_INVALID, "merge produced a global instance id >= bins (num_objs outgrew the histogram; the reference overflows here, tsdf.cu:61,383)");
-			// relabel on the device (LUT) and on the caller's host mask (tsdf.cu:372-389 does it in place)
-			CU(cudaMemcpyAsync(v->d_lut, lut, 256, cudaMemcpyHostToDevice, v->stream));
-			relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(v->d_mask, (int)npx, v->d_lut);
-			LAUNCH_CHECK(v);
+			rc = decide_and_relabel(v, mx, v->d_mask, lut);
+			if (rc) return rc;
 			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
 			if (rc) return rc;
-			// (the LUT copy above is from pageable memory: the runtime stages it before returning)
 			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // overlaps the kernel
 		} else {
 			v->num_objs = mx + 1;  // tsdf.cu:464-467
@@ -1072,10 +1101,7 @@ int sfm_shard_halo(const float *voxel3) {
 	return (int)ceilf(voxel3[0] / voxel3[2]) + 2;
 }
 
-int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
-	const void *d_ev1, const void *d_ev2, void *d_out)
-{
-	if (!v || !s2w16 || !c3 || !d_out || w <= 0 || h <= 0 || stage < 1 || stage > 3) return fail(SFM_ERR_INVALID, "bad argument");
+static int shard_stage(sfm_volume *v, int stage, const RayCam &cam, const void *d_ev1, const void *d_ev2, void *d_out, float4 *hits_out) {
 	if ((stage >= 2 && !d_ev1) || (stage == 3 && !d_ev2)) return fail(SFM_ERR_INVALID, "missing reduced events of the previous stage");
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
 	CU(cudaSetDevice(v->desc.device));
@@ -1085,12 +1111,76 @@ int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const 
 	if ((v->g.own_z0 > 0 && lo_have < halo) || (v->g.own_z0 + v->g.own_nz < v->g.Dz && hi_have < halo))
 		return fail(SFM_ERR_INVALID, "sharded ray-cast needs a halo of " + std::to_string(halo) + " stored planes around the owned range");
 	const RayVol V = make_ray_vol(v);
-	const RayCam cam = make_show_cam(s2w16, c3, w, h);
-	const int blocks = ray_blocks(w, h);
+	const int blocks = ray_blocks(cam.W, cam.H);
 	if (stage == 1) shard_stage1_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (unsigned long long *)d_out);
 	else if (stage == 2) shard_stage2_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (const unsigned long long *)d_ev1, (unsigned long long *)d_out);
-	else shard_stage3_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (const unsigned long long *)d_ev1, (const unsigned long long *)d_ev2, (unsigned long long *)d_out);
+	else shard_stage3_kernel<<<blocks, 128, 0, v->stream>>>(V, cam, (const unsigned long long *)d_ev1, (const unsigned long long *)d_ev2, (unsigned long long *)d_out, hits_out);
 	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
+	const void *d_ev1, const void *d_ev2, void *d_out)
+{
+	if (!v || !s2w16 || !c3 || !d_out || w <= 0 || h <= 0 || stage < 1 || stage > 3) return fail(SFM_ERR_INVALID, "bad argument");
+	return shard_stage(v, stage, make_show_cam(s2w16, c3, w, h), d_ev1, d_ev2, d_out, nullptr);
+}
+
+/* ---- duplicate-instance merge over z-slabs (back_proj_kernel + filter_overlaps, tsdf.cu:426-461) ---- */
+
+int sfm_shard_backproj_stage(sfm_volume *v, int stage, const float *E16, const void *d_ev1, const void *d_ev2, void *d_out) {
+	if (!v || !E16 || !d_out || stage < 1 || stage > 3) return fail(SFM_ERR_INVALID, "bad argument");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = ensure_ray_buffers(v, (size_t)v->W * v->H, false);
+	if (rc) return rc;
+	return shard_stage(v, stage, make_backproj_cam(v, E16), d_ev1, d_ev2, d_out, stage == 3 ? v->d_hits : nullptr);
+}
+
+/* first labelled frame of a sharded volume: no merge yet, num_objs = max(mask) + 1 (tsdf.cu:464-467) */
+int sfm_shard_first_frame(sfm_volume *v, const void *d_mask) {
+	if (!v || !d_mask) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	const size_t npx = (size_t)v->W * v->H;
+	std::vector<uint8_t> m(npx);
+	CU(cudaMemcpyAsync(m.data(), d_mask, npx, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	const int mx = max_label_host(m.data(), npx);
+	if (v->bins > 0 && mx >= v->bins) return fail(SFM_ERR_INVALID, "mask carries a label >= bins");
+	v->num_objs = mx + 1;
+	return SFM_OK;
+}
+
+int sfm_fold_table_bytes(int bins, size_t *bytes_i64, size_t *bytes_total) {
+	if (bins <= 0 || bins > kMaxBins || !bytes_i64 || !bytes_total) return fail(SFM_ERR_INVALID, "bad argument");
+	const FoldLayout fl = fold_layout(bins);
+	*bytes_i64 = fl.oBm;
+	*bytes_total = fl.total;
+	return SFM_OK;
+}
+
+int sfm_shard_fold(sfm_volume *v, const void *d_mask, const void *d_keys_global, int do_counts, void *d_tables) {
+	if (!v || !d_mask || !d_keys_global || !d_tables) return fail(SFM_ERR_INVALID, "null argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	if (!v->d_hits) return fail(SFM_ERR_INVALID, "run sfm_shard_backproj_stage(3) first");
+	CU(cudaSetDevice(v->desc.device));
+	return launch_fold(v, (uint8_t *)d_tables, (const uint8_t *)d_mask, (const unsigned long long *)d_keys_global, do_counts ? 1 : 0);
+}
+
+int sfm_shard_merge_finish(sfm_volume *v, const void *d_tables_reduced, void *d_mask_inout, uint8_t *lut256, sfm_merge_report *report) {
+	if (!v || !d_tables_reduced || !d_mask_inout) return fail(SFM_ERR_INVALID, "null argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	CU(cudaSetDevice(v->desc.device));
+	const int L = v->bins;
+	const FoldLayout fl = fold_layout(L);
+	CU(cudaMemcpyAsync(v->h_fold, d_tables_reduced, fl.total, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	// labels present in the frame: Cm[m] > 0 (pixel counts per incoming label)
+	const unsigned *Cm = (const unsigned *)(v->h_fold + fl.oCm);
+	int mx = 0;
+	for (int m = 1; m < L; m++) if (Cm[m]) mx = m;
+	int rc = decide_and_relabel(v, mx, (uint8_t *)d_mask_inout, lut256);
+	if (rc) return rc;
+	if (report) *report = v->last_merge;
 	return SFM_OK;
 }
 

@@ -249,5 +249,42 @@ class SlabVolume:
         p = packed_dev.data_ptr()
         self.vol.integrate_dev(p + o_d, p + o_c, p + o_m, extrinsic2init)
 
+    def fuse_packed_sharded(self, packed_dev, extrinsic2init, group=None):
+        """Labelled fusion of one frame into a sharded volume = TSDF::launch_kernel (tsdf.cu:418-504) over
+        z-slabs: exact sharded march from the incoming camera (three MIN all-reduces), fold of the hits
+        this rank owns into the overlap tables, SUM all-reduce of the integer tables (exact, so every
+        rank decides on the single-GPU tables), decision + relabel on every rank, integrate.  The label
+        image inside `packed_dev` is relabelled in place; returns (lut, report) -- (None, None) for the
+        first frame, which only fixes num_objs (tsdf.cu:464-467)."""
+        import torch
+        import torch.distributed as dist
+        v = self.vol
+        o_d, o_c, o_m, _ = frame_offsets(self.width, self.height)
+        p = packed_dev.data_ptr()
+        lut = rep = None
+        if v.bins > 0 and v.info().n_obs > 0:
+            dev = packed_dev.device
+            n = self.width * self.height
+            ev1 = torch.empty(n, dtype=torch.int64, device=dev)
+            ev2 = torch.empty(n, dtype=torch.int64, device=dev)
+            keys = torch.empty(n, dtype=torch.int64, device=dev)
+            v.shard_backproj_stage(1, extrinsic2init, None, None, ev1.data_ptr())
+            composite_keys(ev1, group)
+            v.shard_backproj_stage(2, extrinsic2init, ev1.data_ptr(), None, ev2.data_ptr())
+            composite_keys(ev2, group)
+            v.shard_backproj_stage(3, extrinsic2init, ev1.data_ptr(), ev2.data_ptr(), keys.data_ptr())
+            composite_keys(keys, group)
+            n64, ntot = v.fold_table_bytes()
+            tables = torch.empty(ntot, dtype=torch.uint8, device=dev)
+            v.shard_fold(p + o_m, keys.data_ptr(), self.rank == 0, tables.data_ptr())
+            if self.world > 1 and dist.is_initialized():
+                dist.all_reduce(tables[:n64].view(torch.int64), op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(tables[n64:].view(torch.int32), op=dist.ReduceOp.SUM, group=group)
+            lut, rep = v.shard_merge_finish(tables.data_ptr(), p + o_m)
+        elif v.bins > 0:
+            v.shard_first_frame(p + o_m)
+        v.integrate_dev(p + o_d, p + o_c, p + o_m, extrinsic2init)
+        return lut, rep
+
     def close(self):
         self.vol.close()

@@ -201,6 +201,30 @@ class Volume:
                                                C.c_void_p(d_ev1) if d_ev1 else None, C.c_void_p(d_ev2) if d_ev2 else None,
                                                C.c_void_p(d_out)))
 
+    # -- duplicate-instance merge over z-slabs (device pointers; the collectives are the caller's) ----
+    def shard_backproj_stage(self, stage, extrinsic2init, d_ev1, d_ev2, d_out):
+        check(self.lib.sfm_shard_backproj_stage(self._h, stage, _ptr(_f32(extrinsic2init, 16)),
+                                                C.c_void_p(d_ev1) if d_ev1 else None, C.c_void_p(d_ev2) if d_ev2 else None,
+                                                C.c_void_p(d_out)))
+
+    def shard_first_frame(self, d_mask):
+        check(self.lib.sfm_shard_first_frame(self._h, C.c_void_p(d_mask)))
+
+    def fold_table_bytes(self):
+        a, b = C.c_size_t(), C.c_size_t()
+        check(self.lib.sfm_fold_table_bytes(self.bins, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def shard_fold(self, d_mask, d_keys_global, do_counts, d_tables):
+        check(self.lib.sfm_shard_fold(self._h, C.c_void_p(d_mask), C.c_void_p(d_keys_global), int(bool(do_counts)), C.c_void_p(d_tables)))
+
+    def shard_merge_finish(self, d_tables_reduced, d_mask_inout):
+        """-> (lut uint8[256], MergeReport); the device mask is relabelled in place."""
+        lut = np.zeros(256, np.uint8)
+        rep = MergeReport()
+        check(self.lib.sfm_shard_merge_finish(self._h, C.c_void_p(d_tables_reduced), C.c_void_p(d_mask_inout), _ptr(lut), C.byref(rep)))
+        return lut, rep
+
     def keys_to_bgr(self, d_keys, w, h):
         bgr = np.empty((h, w, 3), np.uint8)
         check(self.lib.sfm_keys_to_bgr(self._h, C.c_void_p(d_keys), w, h, _ptr(bgr)))
