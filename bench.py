@@ -8,12 +8,13 @@ Workload (BASELINE.json metric "voxel-updates/s (512^3, 640x480, labeled)"):
   N>1  weak scaling: the same physical cube refined so that every GPU owns 512^3 voxels as one
        z-slab (N=2: 512x512x1024, N=4: 1024x512x1024, N=8: 1024^3 = BASELINE config 3); rank 0
        owns the frames and broadcasts each one over NCCL; no other data-path collective.
-A step = one frame integrated into the volume (K0 prep + K1 integrate).
+A step = one frame integrated into the volume (K0 prep + K1a brick classification + K1b update).
 
   value  device-timed: frames already resident in HBM (rank 0's HBM for N>1, broadcast inside the step)
   e2e    the same metric through the C-ABI call `sfm_integrate_raw` with HOST (pinned) frame
          buffers: H2D copies inside the timed region, U/S counters read back every step
-  roofline  K1's algorithmic bytes (16*U + 14*S + frame + pose) / K1's own CUDA-event time
+  roofline  algorithmic bytes of the step (16*U + 14*S + frame + pose) / CUDA-event time of the
+         dominant kernel (K1b); `frac_incl_classify_kernel` divides by K1a + K1b instead
   cpu_baseline  the reference's NumPy TSDF_Python integrate (restated in oracle/tsdf_numpy.py) on a
          bounded sample of the same workload, timed on this box's host cores
 `--impl reference` runs only that CPU arm and prints the same line shape.
