@@ -44,3 +44,20 @@ def backproj_camera(E):
 
 def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
+
+
+class _DevMem:
+    """Raw device memory as a __cuda_array_interface__ object (so torch can view a library-owned plane)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_plane(vol, name):
+    """torch view (no copy) of one plane of a Volume, shaped like `download(name)`."""
+    import torch
+    _, dt, tail = vol._PLANE[name]
+    tail = (vol.bins,) if tail is None else tail
+    t = torch.as_tensor(_DevMem(vol.plane_ptr(name), vol.plane_bytes(name)), device="cuda")
+    tdt = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8, np.uint32: torch.int32}[dt]
+    return t.view(tdt).reshape(vol.local_shape + tail)
