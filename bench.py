@@ -480,19 +480,27 @@ def run_ours(args):
             vol2.synchronize()
             b0 = vol2.launch_count()
             per_frame = []
-            for i in range(1, nf):
+            half = max(2, nf // 2)
+            for i in range(1, half):  # synchronised after every frame: latency of one labelled frame
                 fr = frames2[i]
                 t0 = time.perf_counter()
                 vol2.fuse_frame(fr["depth"], fr["color"], masks[i], fr["extrinsic"])
                 vol2.synchronize()
                 per_frame.append(time.perf_counter() - t0)
-            dt = float(np.sum(per_frame))
+            t0 = time.perf_counter()
+            for i in range(half, nf):  # back to back: the call returns once the merge decision is known, the
+                fr = frames2[i]        # integrate kernels of frame i overlap the host work and upload of frame i+1
+                vol2.fuse_frame(fr["depth"], fr["color"], masks[i], fr["extrinsic"])
+            vol2.synchronize()
+            piped = (time.perf_counter() - t0) / max(nf - half, 1)
             med = float(np.median(per_frame))
-            fused = {"frames": nf - 1, "ms_per_frame": 1e3 * med, "ms_per_frame_mean": 1e3 * dt / (nf - 1),
-                     "voxel_updates_per_s": int(np.prod(dims)) / med,
+            fused = {"frames": nf - 1, "ms_per_frame": 1e3 * med, "ms_per_frame_back_to_back": 1e3 * piped,
+                     "voxel_updates_per_s": int(np.prod(dims)) / piped,
                      "num_objs": int(vol2.info().num_objs), "instances_in_scene": 8, "launches": vol2.launch_count() - b0,
                      "min_decision_margin": float(vol2.last_merge().margin),
-                     "what": "sfm_fuse_frame per frame (median wall clock, synchronised after every frame, pageable host buffers): H2D + march + fold (K2) + D2H of the L*L tables + host decision + relabel + K0 + K1"}
+                     "what": "sfm_fuse_frame (pageable host buffers): H2D + march + fold (K2) + on-device decision + relabel + K0 + K1a + K1b; "
+                             "ms_per_frame = median wall clock with a synchronise after every frame, ms_per_frame_back_to_back = frames issued "
+                             "back to back (the call returns when the 2 KB merge report is on the host)"}
             vol2.close()
         except Exception as e:  # reported, never hidden
             fused = {"error": str(e)}

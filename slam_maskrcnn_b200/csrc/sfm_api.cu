@@ -138,6 +138,8 @@ struct sfm_volume {
 	size_t probs_px = 0;    // capacity of probs/box
 	// merge scratch
 	uint8_t *d_fold = nullptr;
+	void *d_merge = nullptr, *h_merge = nullptr;  // MergeOut of the device-side decision (+ pinned mirror)
+	cudaEvent_t ev_merge = nullptr;
 	uint8_t *h_fold = nullptr;  // pinned mirror
 	size_t fold_bytes = 0;
 	unsigned long long *h_stats = nullptr;  // pinned
@@ -518,8 +520,8 @@ int launch_fold(sfm_volume *v, uint8_t *d_tables, const uint8_t *d_mask, const u
 	return SFM_OK;
 }
 
-// launch the fused back-project + fold on the device mask; tables end up in v->h_fold (pinned)
-int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
+// enqueue the fused back-project + fold on the device mask; tables end up in v->d_fold
+int enqueue_march_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	const RayVol V = make_ray_vol(v);
 	const RayCam cam = make_backproj_cam(v, E16);
 	const int npix = v->W * v->H;
@@ -527,34 +529,15 @@ int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	if (rc) return rc;
 	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr);
 	LAUNCH_CHECK(v);
-	rc = launch_fold(v, v->d_fold, d_mask, nullptr, 1);
+	return launch_fold(v, v->d_fold, d_mask, nullptr, 1);
+}
+
+// the same, then the tables are copied to v->h_fold (pinned) and the stream is synchronised (parity hook)
+int run_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
+	int rc = enqueue_march_fold(v, E16, d_mask);
 	if (rc) return rc;
 	CU(cudaMemcpyAsync(v->h_fold, v->d_fold, fold_layout(v->bins).total, cudaMemcpyDeviceToHost, v->stream));
 	CU(cudaStreamSynchronize(v->stream));
-	return SFM_OK;
-}
-
-// tables in v->h_fold -> decision -> relabel of the device mask; lut_out[256] (optional) gets the map
-int decide_and_relabel(sfm_volume *v, int mx, uint8_t *d_mask, uint8_t *lut_out) {
-	const int L = v->bins;
-	const size_t npx = (size_t)v->W * v->H;
-	std::vector<double> A((size_t)L * L);
-	std::vector<uint32_t> C((size_t)L * L);
-	combine_tables(v, mx + 1, A.data(), C.data());
-	const unsigned *first = (const unsigned *)(v->h_fold + fold_layout(L).oFirst);
-	sfm_merge_report rep;
-	decide(v, A.data(), C.data(), mx + 1, first, &v->num_objs, &rep);
-	v->last_merge = rep;
-	int newmax = 0;
-	uint8_t lut[256];
-	for (int m = 0; m < 256; m++) { lut[m] = (uint8_t)rep.assign[m]; if (m <= mx) newmax = std::max(newmax, rep.assign[m]); }
-	if (newmax >= L)
-		return fail(SFM_ERR_INVALID, "merge produced a global instance id >= bins (num_objs outgrew the histogram; the reference overflows here, tsdf.cu:61,383)");
-	// relabel on the device (LUT); the copy is from pageable memory: the runtime stages it before returning
-	CU(cudaMemcpyAsync(v->d_lut, lut, 256, cudaMemcpyHostToDevice, v->stream));
-	relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(d_mask, (int)npx, v->d_lut);
-	LAUNCH_CHECK(v);
-	if (lut_out) memcpy(lut_out, lut, 256);
 	return SFM_OK;
 }
 
@@ -635,6 +618,123 @@ void decide(const sfm_volume *v, const double *A, const uint32_t *C, int max_obj
 __global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) mask[i] = lut[mask[i]];
+}
+
+// Decision half of filter_overlaps (tsdf.cu:335-389) on the device, from the folded integer tables: the same
+// statements as decide() + combine_tables() above, one thread per incoming label for the arg-max over the
+// volume's instances (tsdf.cu:340-348), thread 0 for the sequential parts (collisions keep the larger
+// probability, tsdf.cu:349-362; fresh ids in raster order of first appearance, tsdf.cu:378-387).  Writes the
+// 256-entry label map the relabel kernel uses, so a frame's merge needs no host round trip before its
+// integration; the host only reads the 2 KB report back (it relabels the caller's copy of the mask).
+struct MergeOut {
+	sfm_merge_report rep;
+	uint8_t lut[256];
+	int32_t overflow;  // a global id reached `bins` (the reference overflows its histogram there)
+};
+
+__global__ void __launch_bounds__(256) decide_kernel(FoldTables tb, int L, float prior, float accept_factor, long long logprior_fx,
+	int num_objs_in, MergeOut *__restrict__ out)
+{
+	__shared__ int s_best[256];
+	__shared__ float s_bp[256], s_second[256];
+	__shared__ int s_max_obj;
+	const int m = threadIdx.x;
+	if (m == 0) {
+		int mx = 0;
+		for (int k = 1; k < L; k++) if (tb.Cm[k]) mx = k;
+		s_max_obj = mx + 1;
+	}
+	__syncthreads();
+	const int max_obj_now = s_max_obj;
+	int best = -1;
+	float bp = 0.f, second = 0.f;
+	if (m >= 1 && m < max_obj_now && m < L) {
+		for (int j = 1; j < L; j++) {
+			const long long a = tb.Pos[(size_t)m * L + j] + (long long)tb.NoHit[m] * logprior_fx + tb.T[j] - tb.Tm[(size_t)m * L + j];
+			const unsigned c = tb.Cm[m] + tb.B[j] - tb.Bm[(size_t)m * L + j];
+			const float A = (float)((double)a / 4294967296.0);
+			const float p = (c == 0) ? 0.f : expf(A / (float)c);
+			if (p > bp) { second = bp; best = j; bp = p; }
+			else if (p > second) second = p;
+		}
+	}
+	s_best[m] = best; s_bp[m] = bp; s_second[m] = second;
+	__syncthreads();
+	if (m != 0) return;
+	sfm_merge_report &rep = out->rep;
+	const float thr = accept_factor * prior;
+	float margin = INFINITY;
+	int owner[256];
+	float owner_p[256];
+	for (int k = 0; k < 256; k++) { owner[k] = 0; owner_p[k] = 0.f; rep.assign[k] = 0; rep.best_prob[k] = 0.f; }
+	rep.max_obj_now = max_obj_now;
+	for (int k = 1; k < max_obj_now && k < L; k++) {
+		const float kbp = s_bp[k];
+		const int kb = s_best[k];
+		rep.best_prob[k] = kbp;
+		if (tb.FirstPix[k] != 0xffffffffu) {  // only labels present in the frame decide anything visible
+			margin = fminf(margin, fabsf(kbp - thr));
+			if (kbp > thr) margin = fminf(margin, kbp - s_second[k]);
+		}
+		if (kbp > thr) {
+			if (owner[kb] == 0) { owner[kb] = k; owner_p[kb] = kbp; }
+			else {
+				margin = fminf(margin, fabsf(owner_p[kb] - kbp));
+				if (owner_p[kb] < kbp) { owner[kb] = k; owner_p[kb] = kbp; }
+			}
+		}
+	}
+	for (int j = 1; j < 256; j++) if (owner[j]) rep.assign[owner[j]] = j;
+	// unassigned labels that occur get fresh ids in raster order of first appearance: repeated selection of
+	// the smallest first-pixel index among them (at most 255 labels)
+	int num_objs = num_objs_in;
+	for (;;) {
+		unsigned bestpix = 0xffffffffu;
+		int bestm = 0;
+		for (int k = 1; k < max_obj_now && k < L; k++)
+			if (!rep.assign[k] && tb.FirstPix[k] < bestpix) { bestpix = tb.FirstPix[k]; bestm = k; }
+		if (!bestm) break;
+		rep.assign[bestm] = num_objs++;
+	}
+	rep.num_objs = num_objs;
+	rep.margin = margin;
+	int newmax = 0;
+	for (int k = 0; k < 256; k++) {
+		out->lut[k] = (uint8_t)rep.assign[k];
+		if (k < max_obj_now) newmax = max(newmax, rep.assign[k]);
+	}
+	out->overflow = newmax >= L ? 1 : 0;
+}
+
+static_assert(sizeof(MergeOut) <= 4096, "MergeOut buffer");
+
+// Enqueue: decision on the tables at d_tables -> label map -> relabel of the device mask.  Nothing here
+// waits for the GPU; finish_device_decision() later fetches the report.
+int enqueue_device_decision(sfm_volume *v, uint8_t *d_tables, uint8_t *d_mask) {
+	const int L = v->bins;
+	const size_t npx = (size_t)v->W * v->H;
+	const FoldTables tb = fold_tables_at(d_tables, L);
+	const long long logprior_fx = llrint((double)logf(v->desc.prior_err_rate) * 4294967296.0);
+	MergeOut *out = (MergeOut *)v->d_merge;
+	decide_kernel<<<1, 256, 0, v->stream>>>(tb, L, v->desc.prior_err_rate, v->desc.accept_factor, logprior_fx, v->num_objs, out);
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(v->h_merge, v->d_merge, sizeof(MergeOut), cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaEventRecord(v->ev_merge, v->stream));
+	relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(d_mask, (int)npx, out->lut);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+// Wait for the report of the decision enqueued last (not for the kernels behind it), update num_objs.
+int finish_device_decision(sfm_volume *v, uint8_t *lut_out) {
+	CU(cudaEventSynchronize(v->ev_merge));
+	const MergeOut *out = (const MergeOut *)v->h_merge;
+	v->last_merge = out->rep;
+	if (lut_out) memcpy(lut_out, out->lut, 256);
+	if (out->overflow)
+		return fail(SFM_ERR_INVALID, "merge produced a global instance id >= bins (num_objs outgrew the histogram; the reference overflows here, tsdf.cu:61,383)");
+	v->num_objs = out->rep.num_objs;
+	return SFM_OK;
 }
 
 }  // namespace
@@ -823,6 +923,9 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		v->fold_bytes = fold_layout(v->bins).total;
 		CU_OR_DESTROY(cudaMalloc(&v->d_fold, v->fold_bytes));
 		CU_OR_DESTROY(cudaMallocHost(&v->h_fold, v->fold_bytes));
+		CU_OR_DESTROY(cudaMalloc(&v->d_merge, 4096));
+		CU_OR_DESTROY(cudaMallocHost(&v->h_merge, 4096));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_merge, cudaEventDisableTiming));
 	}
 #undef CU_OR_DESTROY
 	*out = v;
@@ -854,6 +957,9 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->h_stats) cudaFreeHost(v->h_stats);
 	if (v->h_err) cudaFreeHost(v->h_err);
 	if (v->h_fold) cudaFreeHost(v->h_fold);
+	cudaFree(v->d_merge);
+	if (v->h_merge) cudaFreeHost(v->h_merge);
+	if (v->ev_merge) cudaEventDestroy(v->ev_merge);
 	if (v->ev_t0) cudaEventDestroy(v->ev_t0);
 	if (v->ev_t1) cudaEventDestroy(v->ev_t1);
 	for (int i = 0; i < sfm_volume::kRing; i++) {
@@ -993,14 +1099,19 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 			// tsdf.cu:426-461: back-project, fold, decide, relabel
 			rc = require_full_volume(v, "sfm_fuse_frame (merge)");
 			if (rc) return rc;
-			rc = run_fold(v, E16, v->d_mask);
+			// everything up to the integration is enqueued without a host round trip: march, fold, decision
+			// and relabel on the device; the host only waits for the 2 KB report to relabel ITS copy of the
+			// mask, which overlaps the integrate kernels
+			rc = enqueue_march_fold(v, E16, v->d_mask);
 			if (rc) return rc;
-			uint8_t lut[256];
-			rc = decide_and_relabel(v, mx, v->d_mask, lut);
+			rc = enqueue_device_decision(v, v->d_fold, v->d_mask);
 			if (rc) return rc;
 			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
 			if (rc) return rc;
-			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // overlaps the kernel
+			uint8_t lut[256];
+			rc = finish_device_decision(v, lut);
+			if (rc) return rc;
+			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // tsdf.cu:372-389 does it in place
 		} else {
 			v->num_objs = mx + 1;  // tsdf.cu:464-467
 			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
@@ -1168,17 +1279,11 @@ int sfm_shard_fold(sfm_volume *v, const void *d_mask, const void *d_keys_global,
 
 int sfm_shard_merge_finish(sfm_volume *v, const void *d_tables_reduced, void *d_mask_inout, uint8_t *lut256, sfm_merge_report *report) {
 	if (!v || !d_tables_reduced || !d_mask_inout) return fail(SFM_ERR_INVALID, "null argument");
-	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	if (v->bins <= 0 || !v->d_merge) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
 	CU(cudaSetDevice(v->desc.device));
-	const int L = v->bins;
-	const FoldLayout fl = fold_layout(L);
-	CU(cudaMemcpyAsync(v->h_fold, d_tables_reduced, fl.total, cudaMemcpyDeviceToHost, v->stream));
-	CU(cudaStreamSynchronize(v->stream));
-	// labels present in the frame: Cm[m] > 0 (pixel counts per incoming label)
-	const unsigned *Cm = (const unsigned *)(v->h_fold + fl.oCm);
-	int mx = 0;
-	for (int m = 1; m < L; m++) if (Cm[m]) mx = m;
-	int rc = decide_and_relabel(v, mx, (uint8_t *)d_mask_inout, lut256);
+	int rc = enqueue_device_decision(v, (uint8_t *)d_tables_reduced, (uint8_t *)d_mask_inout);
+	if (rc) return rc;
+	rc = finish_device_decision(v, lut256);
 	if (rc) return rc;
 	if (report) *report = v->last_merge;
 	return SFM_OK;
