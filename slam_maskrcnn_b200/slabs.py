@@ -118,6 +118,37 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
             best, hi = c, mid
         else:
             lo = mid
+    cap = worst(best) + 1e-12
+
+    # The min-max partition is not unique (one unsplittable chunk can set the bound and leave the greedy
+    # sweep free to overfill the other slabs up to it).  Second pass: every slab aims at an even share of
+    # what is left, never exceeds the bound, and always leaves a remainder the later slabs can hold.
+    def feasible(i, slabs_left):
+        for _ in range(slabs_left):
+            acc, n = 0.0, 0
+            while i < nchunks and n < max_c and (n == 0 or acc + cost[i] <= cap):
+                acc += cost[i]
+                i += 1
+                n += 1
+        return i == nchunks
+
+    cuts, i = [0], 0
+    for r in range(world):
+        left = world - r - 1
+        desired = cost[i:].sum() / (world - r)
+        acc, n = 0.0, 0
+        while i + n < nchunks - left and n < max_c:
+            c = cost[i + n]
+            if n > 0 and acc + c > cap:
+                break
+            if n > 0 and acc + 0.5 * c > desired and feasible(i + n, left):
+                break
+            acc += c
+            n += 1
+        i += n
+        cuts.append(i)
+    if i == nchunks and all(b > a for a, b in zip(cuts, cuts[1:])) and worst(cuts) <= cap:
+        best = cuts
     return [(best[r] * align, (best[r + 1] - best[r]) * align) for r in range(world)]
 
 

@@ -113,3 +113,84 @@ def test_slab_planner_balances_a_front_loaded_profile():
         equal = [prof[i * dz // world:(i + 1) * dz // world].sum() * world for i in range(world)]
         assert max(loads) < 1.2 and max(loads) < max(equal)
     assert plan_slabs(512, 2) == [(0, 256), (256, 256)]
+
+
+def test_slab_planner_splits_a_wall_over_thin_slabs():
+    """A fronto-parallel wall puts most of the cost into ~10 planes: the plan must give them to thin slabs of
+    their own instead of letting one rank own all of them plus free space."""
+    from slam_maskrcnn_b200.slabs import plan_slabs, refine_profile
+    dz, world = 1024, 8
+    prof = np.full(dz, 0.03)
+    prof[:680] += 1.0          # free space in front of the wall
+    prof[672:688] += 40.0      # the wall's truncation band
+    prof /= prof.sum()
+    plan = plan_slabs(dz, world, prof)
+    assert plan[0][0] == 0 and sum(n for _, n in plan) == dz
+    assert all(n % 8 == 0 and 0 < n <= 3 * dz // world for _, n in plan)
+    loads = np.array([prof[z0:z0 + n].sum() for z0, n in plan])
+    wall_owners = [r for r, (z0, n) in enumerate(plan) if z0 < 688 and z0 + n > 672]
+    assert len(wall_owners) >= 2, plan
+    chunk_max = prof.reshape(-1, 8).sum(1).max()  # an 8-plane chunk cannot be split
+    assert loads.max() <= chunk_max + 1e-9, (plan, loads)
+    others = [l for r, l in enumerate(loads) if r not in wall_owners]
+    assert max(others) < 1.3 / world, (plan, loads)
+    # calibration: rescaling keeps the shape inside a slab, moves mass between slabs, stays normalised
+    t = np.ones(world)
+    t[wall_owners[0]] = 3.0
+    prof2 = refine_profile(prof, plan, t)
+    assert abs(prof2.sum() - 1.0) < 1e-12
+    z0, n = plan[wall_owners[0]]
+    assert prof2[z0:z0 + n].sum() == pytest.approx(3.0 / t.sum())
+    seg, seg2 = prof[z0:z0 + n], prof2[z0:z0 + n]
+    assert np.allclose(seg / seg.sum(), seg2 / seg2.sum())
+    plan2 = plan_slabs(dz, world, prof2)
+    assert plan2[wall_owners[0]][1] <= n  # the slab that measured slow does not grow
+
+
+def _table_worker(rank, world, port, q):
+    """The sharded merge's only SUM collective: int64 fixed-point tables + int32 counts, with FirstPix carried by
+    rank 0 alone (zeros elsewhere) -- the layout sfm_shard_fold / SlabVolume.fuse_packed_sharded use."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = 16
+        n64 = (2 * L * L + L) * 8
+        n32 = (L * L + 4 * L) * 4
+        rng = np.random.default_rng(11)
+        parts64 = rng.integers(-2 ** 40, 2 ** 40, (world, n64 // 8), dtype=np.int64)
+        parts32 = rng.integers(0, 2 ** 20, (world, n32 // 4), dtype=np.int64).astype(np.int32)
+        first = np.full(L, -1, np.int32)            # 0xffffffff = label absent
+        first[1:5] = [77, 3, 900, 12]
+        parts32[:, -L:] = 0
+        parts32[0, -L:] = first                      # only the counting rank carries FirstPix
+        buf = torch.zeros(n64 + n32, dtype=torch.uint8)
+        buf[:n64].view(torch.int64).copy_(torch.from_numpy(parts64[rank]))
+        buf[n64:].view(torch.int32).copy_(torch.from_numpy(parts32[rank]))
+        dist.all_reduce(buf[:n64].view(torch.int64), op=dist.ReduceOp.SUM)
+        dist.all_reduce(buf[n64:].view(torch.int32), op=dist.ReduceOp.SUM)
+        ok64 = bool((buf[:n64].view(torch.int64).numpy() == parts64.sum(0)).all())
+        got32 = buf[n64:].view(torch.int32).numpy()
+        ok32 = bool((got32[:-L] == parts32[:, :-L].sum(0, dtype=np.int32)).all())
+        ok_first = bool((got32[-L:] == first).all())
+        q.put((rank, ok64, ok32, ok_first))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_integer_table_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_table_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert all(r[1:]), f"rank {r[0]}: (int64 sum, int32 sum, first-pixel) = {r[1:]}"
