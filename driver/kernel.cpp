@@ -136,7 +136,7 @@ static double stamp_of(const string &fn) {
 }
 
 int main(int argc, char **argv) {
-	string root = ".", render = "render.ppm";
+	string root = ".", render = "render.ppm", render_color, ply;
 	double begin = 68164, end = 68170;  // kernel.cpp:60-61
 	int max_frames = 100, dim = 256, bins = MAX_OBJECTS, views = 10;
 	float intr[4] = {520.9f, 521.0f, 325.1f, 249.7f};  // kernel.cpp:39
@@ -150,6 +150,8 @@ int main(int argc, char **argv) {
 		else if (a == "--max-frames") max_frames = atoi(next().c_str());
 		else if (a == "--views") views = atoi(next().c_str());
 		else if (a == "--render") render = next();
+		else if (a == "--render-color") render_color = next();
+		else if (a == "--ply") ply = next();
 		else root = a;
 	}
 	try {
@@ -203,6 +205,24 @@ int main(int argc, char **argv) {
 			for (size_t p = 0; p < (size_t)img.rows * img.cols; p++) lit += (img.data[p * 3] | img.data[p * 3 + 1] | img.data[p * 3 + 2]) != 0;
 			write_ppm_bgr(render, img);
 			cout << "rendered " << views << " views, last one -> " << render << " (" << lit << " labelled pixels)" << endl;
+			if (!render_color.empty()) {  // the colour mode the reference keeps commented out (viewer.cu:68)
+				write_ppm_bgr(render_color, viewer->show_tsdf_color(*tsdf, angle, tsdf->mean_depth_));
+				cout << "colour view -> " << render_color << endl;
+			}
+		}
+		if (!ply.empty()) {  // surface export: zero-crossing points with colour and label
+			vector<float> xyz;
+			vector<uint8_t> bgr, label;
+			const size_t n = tsdf->extract_surface(xyz, bgr, label);
+			ofstream f(ply, ios::binary);
+			f << "ply\nformat binary_little_endian 1.0\nelement vertex " << n
+			  << "\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar label\nend_header\n";
+			for (size_t i = 0; i < n; i++) {
+				f.write((const char *)&xyz[i * 3], 12);
+				const uint8_t rec[4] = {bgr[i * 3 + 2], bgr[i * 3 + 1], bgr[i * 3], label[i]};
+				f.write((const char *)rec, 4);
+			}
+			cout << "surface: " << n << " points -> " << ply << endl;
 		}
 	} catch (const string &e) {  // the reference throws std::string (tsdf.cu:502, viewer.cu:174)
 		cerr << e << endl;

@@ -183,6 +183,20 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 int sfm_shard_raycast_stage(sfm_volume *v, int stage, const float *s2w16, const float *c3, int w, int h,
 	const void *d_ev1, const void *d_ev2, void *d_out);
 int sfm_shard_halo(const float *voxel3);
+/* Colour render mode: the marcher of sfm_raycast with interp_tsdf_color (utils.cu:121-142) at the hit -- the
+ * call the reference keeps commented out at viewer.cu:68.  bgr: u8[h][w][3] in the colour plane's channel
+ * order, zero where no surface is hit; t_opt (optional): refined t per ray; xyzt_opt (optional): f32[h][w][4]
+ * hit position in the volume's frame + t (all zero where no surface is hit). */
+int sfm_raycast_color(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, uint8_t *bgr, float *t_opt, float *xyzt_opt);
+int sfm_show_color(sfm_volume *v, float angle, float dist, int w, int h, uint8_t *bgr);  /* Viewer::show_tsdf's orbit camera */
+
+/* Surface export (no reference counterpart: the reference can only look at the volume through its viewer
+ * window).  One point per voxel edge (+x, +y, +z) between two observed voxels whose SDF values differ in
+ * sign, at the linear zero crossing; colour and arg-max label of the end voxel nearer to the crossing.
+ * *count receives the number of crossings found (it may exceed max_points; only the first max_points, in
+ * arbitrary order, are written -- call with max_points = 0 to size the buffers). */
+int sfm_extract_surface(sfm_volume *v, uint32_t max_points, float *xyz, uint8_t *bgr, uint8_t *label, uint32_t *count);
+
 /* Duplicate-instance merge over z-slabs (tsdf.cu:426-461 on a sharded volume).  Per frame and rank:
  *   1. sfm_shard_backproj_stage(v, 1|2|3, extrinsic2init, ...) -- the three stages of the exact sharded march
  *      (see sfm_shard_raycast_stage) from the INCOMING camera; the caller MIN-all-reduces each stage's

@@ -99,6 +99,14 @@ public:
 	void get_voxel(float out[3]) const { sfm_info i = info(); memcpy(out, i.voxel, 12); }
 	const float *get_intrinsic() const { return desc_.K; }
 	sfm_info info() const { sfm_info i; sfm::check(sfm_get_info(vol_, &i)); return i; }
+	// zero-crossing points of the fused volume (no reference counterpart): xyz[3n], bgr[3n], label[n]
+	size_t extract_surface(std::vector<float> &xyz, std::vector<uint8_t> &bgr, std::vector<uint8_t> &label) const {
+		uint32_t n = 0;
+		sfm::check(sfm_extract_surface(vol_, 0, nullptr, nullptr, nullptr, &n));
+		xyz.resize((size_t)n * 3); bgr.resize((size_t)n * 3); label.resize(n);
+		if (n) sfm::check(sfm_extract_surface(vol_, n, xyz.data(), bgr.data(), label.data(), &n));
+		return n;
+	}
 	sfm_volume *handle() const { return vol_; }
 	// the reference exposes its device pointers as public members (tsdf.cuh:24-43)
 	float *tsdf_diff_d() const { return (float *)sfm_plane_device_ptr(vol_, SFM_PLANE_SDF); }
@@ -132,6 +140,12 @@ public:
 	sfm::Mat show_tsdf(const TSDF &tsdf, float angle, float dist) {
 		sfm::Mat img(height_, width_, 3, 1);
 		sfm::check(sfm_show(tsdf.handle(), angle, dist, width_, height_, img.data));
+		return img;
+	}
+	// the same orbit view in colour mode: interp_tsdf_color at the hit (the call viewer.cu:68 keeps commented out)
+	sfm::Mat show_tsdf_color(const TSDF &tsdf, float angle, float dist) {
+		sfm::Mat img(height_, width_, 3, 1);
+		sfm::check(sfm_show_color(tsdf.handle(), angle, dist, width_, height_, img.data));
 		return img;
 	}
 };

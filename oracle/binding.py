@@ -188,6 +188,17 @@ def ref_back_proj(bins, Kinv, Rt, o, start, end, voxel, dims, sdf_d, cnt_d, w, h
     assert rc == 0, "reference back_proj_kernel failed"
 
 
+def ref_color_at(bins, xyz_d, valid_d, n, start, voxel, dims, color_d, out_d):
+    """The reference's interp_tsdf_color (utils.cu:121-142) at n positions (device pointers)."""
+    lib = ref(bins)
+    if not hasattr(lib, "ref_color_at"):
+        return False
+    rc = lib.ref_color_at(_vp(xyz_d), _vp(valid_d), C.c_int(n), _p(_f32(start, 3)), _p(_f32(voxel, 3)), _p(_i32(dims)),
+                          _vp(color_d), _vp(out_d))
+    assert rc == 0, "reference interp_tsdf_color failed"
+    return True
+
+
 def ref_show(bins, s2w, c, start, end, voxel, dims, sdf_d, color_d, cnt_d, w, h, out_d, palette):
     lib = ref(bins)
     pal = np.ascontiguousarray(palette, np.uint8)

@@ -32,6 +32,18 @@ __global__ void show_tsdf_kernel(float *s2w, float3 *c, float3 *vol_start, float
 	int3 *vol_dim, float *tsdf_diff, uchar3 *tsdf_color, uint32_t *tsdf_cnt,
 	int width, int height, uchar3 *output, uint8_t *random_colors);
 
+// the reference's colour sampler (utils.cu:121-142): defined in the generated utils TU, unused by the
+// reference's own kernels (its only call, viewer.cu:68, is commented out) -- launched from a shim kernel here
+__device__ uchar3 interp_tsdf_color(const float3 &pos, const float3 &vol_start, const float3 &voxel, const int3 &vol_dim, uchar3 *tsdf_color);
+
+__global__ void shim_color_at_kernel(const float *xyz, const uint8_t *valid, int n, float3 vol_start, float3 voxel, int3 vol_dim,
+	uchar3 *tsdf_color, uchar3 *out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !valid[i]) return;
+	out[i] = interp_tsdf_color(make_float3(xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]), vol_start, voxel, vol_dim, tsdf_color);
+}
+
 // defined in the generated overlaps TU (verbatim TSDF::filter_overlaps behind a cv::Mat shim)
 extern "C" int ref_filter_overlaps_impl(float *probs, int width, int height, uint8_t *mask,
 	bool *box_mask, uint32_t n_obs, int *num_objs_inout);
@@ -134,6 +146,15 @@ int ref_show(const float *s2w16, const float *c3,
 		(float3 *)(g_s.f + 24), (float3 *)(g_s.f + 28), (int3 *)g_s.i, sdf_d, (uchar3 *)color_d, cnt_d,
 		width, height, (uchar3 *)out_bgr_d, g_s.pal);
 	return finish("show_tsdf_kernel");
+}
+
+// the reference's interp_tsdf_color at n given positions (device pointers; out must be zero-filled)
+int ref_color_at(const float *xyz_d, const uint8_t *valid_d, int n, const float *vol_start, const float *voxel, const int *dims,
+	uint8_t *color_d, uint8_t *out_d)
+{
+	shim_color_at_kernel<<<(n + 127) / 128, 128>>>(xyz_d, valid_d, n, make_float3(vol_start[0], vol_start[1], vol_start[2]),
+		make_float3(voxel[0], voxel[1], voxel[2]), make_int3(dims[0], dims[1], dims[2]), (uchar3 *)color_d, (uchar3 *)out_d);
+	return finish("interp_tsdf_color");
 }
 
 // CPU: verbatim TSDF::filter_overlaps (tsdf.cu:304-416).  All pointers are host pointers.

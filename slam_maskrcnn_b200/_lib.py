@@ -93,6 +93,9 @@ SYMBOLS = {
     "sfm_integrate_times": (_i, [_vp, _vp, _i]),
     "sfm_frame_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_stats_begin": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "sfm_raycast_color": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sfm_show_color": (_i, [_vp, _f, _f, _i, _i, _vp]),
+    "sfm_extract_surface": (_i, [_vp, C.c_uint32, _vp, _vp, _vp, C.POINTER(C.c_uint32)]),
     "sfm_shard_backproj_stage": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "sfm_shard_first_frame": (_i, [_vp, _vp]),
     "sfm_fold_table_bytes": (_i, [_i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -1198,6 +1198,58 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	return SFM_OK;
 }
 
+int sfm_raycast_color(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, uint8_t *bgr, float *t_opt, float *xyzt_opt) {
+	if (!v || !s2w16 || !c3 || !bgr || w <= 0 || h <= 0 || w > 65535 || h > 65535) return fail(SFM_ERR_INVALID, "bad argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_raycast_color");
+	if (rc) return rc;
+	const size_t npx = (size_t)w * h;
+	rc = ensure_ray_buffers(v, npx, false);
+	if (rc) return rc;
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags);
+	LAUNCH_CHECK(v);
+	shade_color_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), v->planes.color, (int)npx, v->d_hits, v->d_bgr, v->d_t);
+	LAUNCH_CHECK(v);
+	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));
+	if (t_opt) CU(cudaMemcpyAsync(t_opt, v->d_t, npx * 4, cudaMemcpyDeviceToHost, v->stream));
+	if (xyzt_opt) CU(cudaMemcpyAsync(xyzt_opt, v->d_hits, npx * 16, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+int sfm_extract_surface(sfm_volume *v, uint32_t max_points, float *xyz, uint8_t *bgr, uint8_t *label, uint32_t *count) {
+	if (!v || !count || (max_points && (!xyz || !bgr || !label))) return fail(SFM_ERR_INVALID, "null argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	SurfaceOut out{};
+	out.max_points = max_points;
+	uint8_t *d_buf = nullptr;
+	const size_t bytes = 16 + (size_t)max_points * 16;
+	CU(cudaMalloc(&d_buf, bytes));
+	out.count = (unsigned *)d_buf;
+	out.xyz = (float *)(d_buf + 16);
+	out.bgr = d_buf + 16 + (size_t)max_points * 12;
+	out.label = d_buf + 16 + (size_t)max_points * 15;
+	cudaError_t e = cudaMemsetAsync(d_buf, 0, 16, v->stream);
+	if (e == cudaSuccess) {
+		extract_surface_kernel<<<v->num_sms * 8, 256, 0, v->stream>>>(v->g, v->planes.sdf, v->planes.wt, v->planes.color, v->planes.hist, v->bins, out);
+		v->launches++;
+		e = cudaGetLastError();
+	}
+	unsigned n = 0;
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&n, out.count, 4, cudaMemcpyDeviceToHost, v->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+	const size_t m = std::min<size_t>(n, max_points);
+	if (e == cudaSuccess && m) e = cudaMemcpy(xyz, out.xyz, m * 12, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && m) e = cudaMemcpy(bgr, out.bgr, m * 3, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && m) e = cudaMemcpy(label, out.label, m, cudaMemcpyDeviceToHost);
+	cudaFree(d_buf);
+	if (e != cudaSuccess) return fail(SFM_ERR_CUDA, cudaGetErrorString(e));
+	*count = n;
+	return SFM_OK;
+}
+
 int sfm_ray_flags(sfm_volume *v, uint8_t *flags, size_t n) {
 	if (!v || !flags) return fail(SFM_ERR_INVALID, "null argument");
 	if (n > v->ray_px) return fail(SFM_ERR_INVALID, "no ray-march of that size has run");
@@ -1318,6 +1370,13 @@ int sfm_show(sfm_volume *v, float angle, float dist, int w, int h, uint8_t *bgr)
 	float s2w[16], c[3];
 	sfm_orbit_camera(v->Kinv, angle, dist, s2w, c);
 	return sfm_raycast(v, s2w, c, w, h, bgr, nullptr, nullptr);
+}
+
+int sfm_show_color(sfm_volume *v, float angle, float dist, int w, int h, uint8_t *bgr) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	float s2w[16], c[3];
+	sfm_orbit_camera(v->Kinv, angle, dist, s2w, c);
+	return sfm_raycast_color(v, s2w, c, w, h, bgr, nullptr, nullptr);
 }
 
 size_t sfm_plane_bytes(sfm_volume *v, int plane) { return v ? v->nvox * plane_elem_bytes(v, plane) : 0; }

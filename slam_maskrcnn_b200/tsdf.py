@@ -201,6 +201,30 @@ class Volume:
                                                C.c_void_p(d_ev1) if d_ev1 else None, C.c_void_p(d_ev2) if d_ev2 else None,
                                                C.c_void_p(d_out)))
 
+    def raycast_color(self, s2w, c, w=None, h=None, want_t=False, want_xyzt=False):
+        """Colour render mode (interp_tsdf_color at the hit, the call viewer.cu:68 keeps commented out)."""
+        w, h = w or self.width, h or self.height
+        bgr = np.empty((h, w, 3), np.uint8)
+        t = np.empty((h, w), np.float32) if want_t else None
+        xyzt = np.empty((h, w, 4), np.float32) if want_xyzt else None
+        check(self.lib.sfm_raycast_color(self._h, _ptr(_f32(s2w, 16)), _ptr(_f32(c, 3)), w, h, _ptr(bgr), _ptr(t), _ptr(xyzt)))
+        out = (bgr,) + ((t,) if want_t else ()) + ((xyzt,) if want_xyzt else ())
+        return out if len(out) > 1 else bgr
+
+    def extract_surface(self):
+        """Zero-crossing points of the fused volume: (xyz float32 [n,3], bgr uint8 [n,3], label uint8 [n]),
+        sorted by position so the result is reproducible."""
+        n = C.c_uint32()
+        check(self.lib.sfm_extract_surface(self._h, 0, None, None, None, C.byref(n)))
+        cap = int(n.value)
+        xyz, bgr, lab = np.empty((cap, 3), np.float32), np.empty((cap, 3), np.uint8), np.empty(cap, np.uint8)
+        if cap:
+            check(self.lib.sfm_extract_surface(self._h, cap, _ptr(xyz), _ptr(bgr), _ptr(lab), C.byref(n)))
+            assert int(n.value) == cap
+            order = np.lexsort((xyz[:, 2], xyz[:, 1], xyz[:, 0]))
+            xyz, bgr, lab = xyz[order], bgr[order], lab[order]
+        return xyz, bgr, lab
+
     # -- duplicate-instance merge over z-slabs (device pointers; the collectives are the caller's) ----
     def shard_backproj_stage(self, stage, extrinsic2init, d_ev1, d_ev2, d_out):
         check(self.lib.sfm_shard_backproj_stage(self._h, stage, _ptr(_f32(extrinsic2init, 16)),
@@ -289,6 +313,26 @@ class Volume:
         u, s = C.c_uint64(), C.c_uint64()
         check(self.lib.sfm_frame_stats(self._h, C.byref(u), C.byref(s)))
         return int(u.value), int(s.value)
+
+
+def write_ply(path, xyz, bgr, label=None):
+    """Binary little-endian PLY point cloud (x y z, red green blue[, label])."""
+    n = len(xyz)
+    fields = [("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")]
+    if label is not None:
+        fields.append(("label", "u1"))
+    rec = np.empty(n, dtype=fields)
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    rec["red"], rec["green"], rec["blue"] = bgr[:, 2], bgr[:, 1], bgr[:, 0]
+    if label is not None:
+        rec["label"] = label
+    names = {"<f4": "float", "u1": "uchar"}
+    with open(path, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % n).encode())
+        for name, dt in fields:
+            f.write(("property %s %s\n" % (names[dt], name)).encode())
+        f.write(b"end_header\n")
+        f.write(rec.tobytes())
 
 
 def orbit_camera(Kinv, angle, dist):
