@@ -135,6 +135,13 @@ int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color
 /* Same with frame buffers already resident in device memory (multi-GPU: after the NCCL broadcast). */
 int sfm_integrate_dev(sfm_volume *v, const void *d_depth, const void *d_color, const void *d_mask,
 	const float *extrinsic2init16);
+/* The same with an explicit statement of WHEN the frame images are valid: `ready_event` is a cudaEvent_t the
+ * producer of the frame recorded (an upload, an ncclBroadcast), or NULL if the images are valid already.
+ * sfm_integrate_dev has to assume they become valid in the order of the handle's stream, which serialises the
+ * frame preparation (tile grids, brick classification: K0 + K1a, which never touch the volume) behind the
+ * previous frame's update kernel; with this call it overlaps it on a second stream. */
+int sfm_integrate_dev_ready(sfm_volume *v, const void *d_depth, const void *d_color, const void *d_mask,
+	const float *extrinsic2init16, void *ready_event);
 
 /* back_proj_kernel (tsdf.cu:72-135, launch 441-455), materialised: probs f32[H*W*bins],
  * box_mask u8[H*W*bins] on the HOST (parity hook; the fused path never builds these).

@@ -101,6 +101,7 @@ SYMBOLS = {
     "sfm_fold_table_bytes": (_i, [_i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sfm_shard_fold": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sfm_shard_merge_finish": (_i, [_vp, _vp, _vp, _vp, C.POINTER(MergeReport)]),
+    "sfm_integrate_dev_ready": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sfm_integrate_times2": (_i, [_vp, _vp, _vp, _i]),
     "sfm_stats_end": (_i, [_vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_debug_divcheck": (_i, [_f, C.c_uint, _i, _i, _f, C.POINTER(C.c_uint64)]),

@@ -127,9 +127,13 @@ __device__ __forceinline__ bool same_bits(const float &a, const float &b) {
 
 enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
 
-#ifndef SFM_K1_MIN_BLOCKS
-#define SFM_K1_MIN_BLOCKS 4  // resident 256-thread blocks per SM K1 is compiled for (register cap 64)
+#ifndef SFM_K1_THREADS
+#define SFM_K1_THREADS 128  // threads per K1b block (7 resident blocks per SM leave room for one K1a block)
 #endif
+#ifndef SFM_K1_MIN_BLOCKS
+#define SFM_K1_MIN_BLOCKS (1024 / SFM_K1_THREADS)  // resident blocks per SM K1b is compiled for (register cap 64)
+#endif
+constexpr int kK1Threads = SFM_K1_THREADS;
 
 constexpr int kSbX = 8;  // super-block: kSbX x-planes x kSbG brick rows x one 32-z chunk = 32 bricks
 constexpr int kSbG = 4;
@@ -345,6 +349,7 @@ constexpr int kFetch = SFM_K1_FETCH;           // bricks a K1b warp takes per fe
 #ifndef SFM_K1_PIPE
 #define SFM_K1_PIPE 0
 #endif
+constexpr int kK1aThreads = 128;               // K1a block size: small enough to run next to a resident wave of K1b
 constexpr int kSbPerBlock = 64;                // most super-blocks one K1a block classifies (sizes its shared lists)
 
 // ---------------------------------------------------------------------------------------------
@@ -354,7 +359,7 @@ constexpr int kSbPerBlock = 64;                // most super-blocks one K1a bloc
 // list.  The tile grids are staged into shared memory once per block by a TMA bulk copy.
 // ---------------------------------------------------------------------------------------------
 template <bool VEC4, bool CULL, bool TMA_TILES>
-__global__ void __launch_bounds__(256) classify_kernel(VolGeom g, FrameView f, WorkLists wl)
+__global__ void __launch_bounds__(kK1aThreads) classify_kernel(VolGeom g, FrameView f, WorkLists wl)
 {
 	const int zsh = VEC4 ? g.zl_log2 : 5;   // log2 lanes along z per column
 	const int CPW = 32 >> zsh;              // columns per brick
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(256) classify_kernel(VolGeom g, FrameView f, W
 // same amount of work to within a few bricks, whatever the geometry of the frame.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool LABELS, bool KCANON>
-__global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
+__global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
 	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err)
 {
 	const int zsh = VEC == 4 ? g.zl_log2 : 5;  // log2 lanes along z per column (3: a brick is 4 columns x 32 planes)
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(256, SFM_K1_MIN_BLOCKS) integrate_kernel(Plane
 	nU = __reduce_add_sync(0xffffffffu, nU);
 	nS = __reduce_add_sync(0xffffffffu, nS);
 	if (lane == 0 && (nU | nS)) {
-		const int slot = (int)((blockIdx.x * 8 + warp) % kStatSlots);
+		const int slot = (int)((blockIdx.x * (kK1Threads / 32) + warp) % kStatSlots);
 		atomicAdd(stats + slot, (unsigned long long)nU);
 		if (nS) atomicAdd(stats + kStatSlots + slot, (unsigned long long)nS);
 	}

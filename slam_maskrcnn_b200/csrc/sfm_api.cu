@@ -110,13 +110,22 @@ struct sfm_volume {
 	unsigned long long *h_stat_ring = nullptr;   // pinned, kStatRing x 2*kStatSlots
 	cudaEvent_t ev_stat[kStatRing] = {};
 	uint64_t stat_tickets = 0;
-	uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
+	// Per-frame preparation contexts, double buffered: what K0 + K1a produce for K1b.  K0 / K1a of frame i+1
+	// run on prep_stream while K1b of frame i still reads the other context on the main stream.
+	struct PrepCtx {
+		uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
+		float *d_depth_m = nullptr;
+		unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
+		uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
+		cudaEvent_t ev_ready = nullptr;  // K1a of the frame that uses this context is done (prep_stream)
+		cudaEvent_t ev_free = nullptr;   // K1b of that frame is done (main stream): the context may be rewritten
+	} ctx[3];
+	static constexpr int kCtx = 3;  // frame i uses ctx[i % 3]: its preparation may start while K1b of frame i-2 still runs
+	cudaStream_t prep_stream = nullptr;
+	cudaEvent_t ev_call = nullptr;
 	size_t tile_bytes = 0;
-	float *d_depth_m = nullptr;
 	unsigned long long *d_stats = nullptr;
 	uint32_t *d_err = nullptr;
-	unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
-	uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
 	size_t nbricks = 0;
 	int num_sms = 148;
 	size_t occ_bytes = 0;
@@ -157,7 +166,8 @@ struct sfm_volume {
 	bool own_stream = false;
 	cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 	static constexpr int kRing = 2048;  // per-call event pairs around K1 (integrate kernel only)
-	cudaEvent_t ev_k0[kRing] = {}, ev_km[kRing] = {}, ev_k1[kRing] = {};  // before K1a | between | after K1b
+	cudaEvent_t ev_k0[kRing] = {}, ev_km[kRing] = {};  // around K1a (prep_stream)
+	cudaEvent_t ev_kb[kRing] = {}, ev_k1[kRing] = {};  // around K1b (main stream)
 	uint64_t n_integrate = 0;
 	uint64_t launches = 0;
 	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
@@ -257,17 +267,17 @@ int release_frame(sfm_volume *v) {
 	return SFM_OK;
 }
 
-FrameView make_frame_view(const sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask,
+FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, const void *d_depth, const void *d_rgb, const void *d_mask,
 	const float *E16)
 {
 	FrameView f{};
 	f.depth = (const uint16_t *)d_depth;
 	f.rgb = (const uint8_t *)d_rgb;
 	f.mask = (const uint8_t *)d_mask;
-	f.tilemax = v->d_tilemax;
-	f.tilemin = v->d_tilemin;
+	f.tilemax = c.d_tilemax;
+	f.tilemin = c.d_tilemin;
 	f.tile_bytes = (unsigned)v->tile_bytes;
-	f.depth_m = v->d_depth_m;
+	f.depth_m = c.d_depth_m;
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
 	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
@@ -300,13 +310,14 @@ void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, lo
 		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		smem_set = smem;
 	}
-	// persistent-ish grid: 4 blocks per SM, more when a block would otherwise see > kSbPerBlock super-blocks
-	const long long want = (nsb + 7) / 8;
-	int blocks = (int)std::max<long long>(std::max(1LL, std::min<long long>(4LL * v->num_sms, want)), (nsb + kSbPerBlock - 1) / kSbPerBlock);
+	// persistent-ish grid: 1024 threads per SM, more blocks when one would otherwise see > kSbPerBlock super-blocks
+	constexpr int warps = kK1aThreads / 32;
+	const long long want = (nsb + warps - 1) / warps;
+	int blocks = (int)std::max<long long>(std::max(1LL, std::min<long long>((1024LL / kK1aThreads) * v->num_sms, want)), (nsb + kSbPerBlock - 1) / kSbPerBlock);
 	// without the TMA staging a block has no set-up cost: one super-block per warp, and the hardware
 	// block scheduler balances the (very uneven) super-block costs
 	if (!TMA_TILES || getenv("SFM_K1A_WIDE")) blocks = (int)std::max(1LL, want);
-	kern<<<blocks, 256, smem, v->stream>>>(v->g, f, wl);
+	kern<<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
 }
 
 template <bool VEC4>
@@ -322,17 +333,21 @@ template <int VEC, bool LABELS, bool KCANON>
 void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
 	// persistent grid: one resident wave (occupancy x SM count); the warps pull bricks from the lists.
 	// dynamic shared memory: the per-warp surface queues
-	const size_t smem = 8 * kQueue * sizeof(uint4);
+	constexpr int warps = kK1Threads / 32;
+	const size_t smem = warps * kQueue * sizeof(uint4);
 	static int per_sm = 0;
 	auto kern = integrate_kernel<VEC, LABELS, KCANON>;
 	if (!per_sm) {
 		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1)
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kK1Threads, smem) != cudaSuccess || per_sm < 1)
 			per_sm = 1;
+		// one block slot per SM is left to K1a of the next frame, which runs concurrently on prep_stream
+		if (per_sm * kK1Threads >= 1024) per_sm = (1024 - kK1aThreads) / kK1Threads;
+		if (const char *e = getenv("SFM_K1B_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
 	}
-	const long long want = ((long long)v->nbricks + 7) / 8;
+	const long long want = ((long long)v->nbricks + warps - 1) / warps;
 	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));
-	kern<<<blocks, 256, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err);
+	kern<<<blocks, kK1Threads, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err);
 }
 
 template <int VEC, bool LABELS>
@@ -347,14 +362,36 @@ void launch_update(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
 	else launch_update2<VEC, LABELS, false>(v, f, wl);
 }
 
-// K0 + K1 on device-resident frame images
-int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16) {
+// K0 + K1a + K1b on device-resident frame images.
+// K0 and K1a (frame preparation: tile grids, depth in metres, brick lists) only read the frame, never the
+// volume, so they run on prep_stream into one of two contexts and overlap K1b of the PREVIOUS frame, which
+// still runs on the main stream (K1b is launched with 7 x 128-thread blocks per SM so that one 128-thread
+// K1a block fits next to them).  `frame_ready` says when the frame images are valid:
+//   kReadyNow      they are valid already (resident frames);
+//   kReadyInOrder  they become valid in main-stream order (caller's earlier work on that stream): the
+//                  preparation then waits for everything issued on the main stream so far -- correct for any
+//                  caller, but serialised behind the previous frame's K1b;
+//   an event       recorded by whoever produces the frame (our own upload on copy_stream, a broadcast).
+const cudaEvent_t kReadyNow = nullptr;
+const cudaEvent_t kReadyInOrder = (cudaEvent_t)(uintptr_t)1;
+
+// first half: K0 + K1a of the next frame on prep_stream (the frame's context is ctx[n_integrate % kCtx])
+int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16, cudaEvent_t frame_ready) {
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set (call sfm_set_bounds / sfm_init_from_frame / sfm_parse_frame first)");
-	const FrameView f = make_frame_view(v, d_depth, d_rgb, d_mask, E16);
+	sfm_volume::PrepCtx &c = v->ctx[v->n_integrate % sfm_volume::kCtx];
+	const FrameView f = make_frame_view(v, c, d_depth, d_rgb, d_mask, E16);
+	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
+	if (frame_ready == kReadyInOrder) {
+		CU(cudaEventRecord(v->ev_call, v->stream));
+		CU(cudaStreamWaitEvent(v->prep_stream, v->ev_call, 0));
+	} else if (frame_ready != kReadyNow) {
+		CU(cudaStreamWaitEvent(v->prep_stream, frame_ready, 0));
+	}
+	CU(cudaStreamWaitEvent(v->prep_stream, c.ev_free, 0));  // K1b of frame i-kCtx has finished with this context
 	const int prep_warps = v->TW * v->TH;
 	const int prep_blocks = (prep_warps * 32 + 255) / 256;
-	prep_frame_kernel<<<prep_blocks, 256, 0, v->stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
-		v->bins, v->desc.depth_scale, v->d_tilemax, v->d_tilemin, v->d_depth_m, v->d_err, v->d_work);
+	prep_frame_kernel<<<prep_blocks, 256, 0, v->prep_stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
+		v->bins, v->desc.depth_scale, c.d_tilemax, c.d_tilemin, c.d_depth_m, v->d_err, c.d_work);
 	LAUNCH_CHECK(v);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one z chunk (k_integrate.cuh)
@@ -362,13 +399,25 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
 	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
 	v->g.brick_mul = 1;
-	const WorkLists wl{v->d_list_mixed, v->d_list_free, v->d_work};
-	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
-	CU(cudaEventRecord(v->ev_k0[slot], v->stream));
+	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
+	CU(cudaEventRecord(v->ev_k0[slot], v->prep_stream));
 	if (vec4) launch_classify<true>(v, f, wl, nsb);
 	else launch_classify<false>(v, f, wl, nsb);
 	LAUNCH_CHECK(v);
-	CU(cudaEventRecord(v->ev_km[slot], v->stream));
+	CU(cudaEventRecord(v->ev_km[slot], v->prep_stream));
+	CU(cudaEventRecord(c.ev_ready, v->prep_stream));
+	return SFM_OK;
+}
+
+// second half: K1b on the main stream, after the context enqueue_prepare filled
+int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16) {
+	sfm_volume::PrepCtx &c = v->ctx[v->n_integrate % sfm_volume::kCtx];
+	const FrameView f = make_frame_view(v, c, d_depth, d_rgb, d_mask, E16);
+	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
+	const bool vec4 = (v->g.nz % 4 == 0);
+	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
+	CU(cudaStreamWaitEvent(v->stream, c.ev_ready, 0));
+	CU(cudaEventRecord(v->ev_kb[slot], v->stream));
 	if (vec4) {
 		if (v->bins > 0) launch_update<4, true>(v, f, wl);
 		else launch_update<4, false>(v, f, wl);
@@ -378,10 +427,19 @@ int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, cons
 	}
 	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_k1[slot], v->stream));
+	CU(cudaEventRecord(c.ev_free, v->stream));
 	v->n_integrate++;
 	v->n_obs++;  // tsdf.cu:220 (counted here so the raw / device entry points keep n_obs consistent)
 	if (v->desc.flags & SFM_FLAG_SYNC_EVERY_CALL) CU(cudaStreamSynchronize(v->stream));
 	return SFM_OK;
+}
+
+int integrate_device(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16,
+	cudaEvent_t frame_ready = kReadyInOrder)
+{
+	int rc = enqueue_prepare(v, d_depth, d_rgb, d_mask, E16, frame_ready);
+	if (rc) return rc;
+	return enqueue_update(v, d_depth, d_rgb, d_mask, E16);
 }
 
 int ensure_ray_buffers(sfm_volume *v, size_t px, bool want_probs) {
@@ -832,6 +890,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	for (int i = 0; i < sfm_volume::kRing; i++) {
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k0[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_km[i]));
+		CU_OR_DESTROY(cudaEventCreate(&v->ev_kb[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k1[i]));
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
@@ -866,15 +925,21 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMallocHost(&v->h_stat_ring, (size_t)sfm_volume::kStatRing * 2 * kStatSlots * 8));
 	for (int i = 0; i < sfm_volume::kStatRing; i++) CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_stat[i], cudaEventDisableTiming));
 	v->tile_bytes = (((size_t)v->TW * v->TH * 4) + 15) / 16 * 16;
-	CU_OR_DESTROY(cudaMalloc(&v->d_tilemax, v->tile_bytes));
-	CU_OR_DESTROY(cudaMemset(v->d_tilemax, 0, v->tile_bytes));
-	v->d_tilemin = v->d_tilemax + (size_t)v->TW * v->TH;
-	CU_OR_DESTROY(cudaMalloc(&v->d_depth_m, npx * 4));
+	CU_OR_DESTROY(cudaStreamCreateWithFlags(&v->prep_stream, cudaStreamNonBlocking));
+	CU_OR_DESTROY(cudaEventCreateWithFlags(&v->ev_call, cudaEventDisableTiming));
+	for (auto &c : v->ctx) {
+		CU_OR_DESTROY(cudaMalloc(&c.d_tilemax, v->tile_bytes));
+		CU_OR_DESTROY(cudaMemset(c.d_tilemax, 0, v->tile_bytes));
+		c.d_tilemin = c.d_tilemax + (size_t)v->TW * v->TH;
+		CU_OR_DESTROY(cudaMalloc(&c.d_depth_m, npx * 4));
+		CU_OR_DESTROY(cudaMalloc(&c.d_work, 16));
+		CU_OR_DESTROY(cudaMemset(c.d_work, 0, 16));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
+		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_free, cudaEventDisableTiming));
+	}
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
-	CU_OR_DESTROY(cudaMalloc(&v->d_work, 16));
-	CU_OR_DESTROY(cudaMemset(v->d_work, 0, 16));
 	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
 		// brick shape on the 128-bit path: 32 planes per brick unless the slab is so thin that more than half the lanes
 		// of such a brick would fall outside it (see VolGeom::zl_log2); SFM_ZL_LOG2 overrides (experiments)
@@ -900,8 +965,10 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 			return fail(SFM_ERR_INVALID, "volume too large for the packed brick ids (x <= 2048, y <= 8192 (2048 when nz % 4 != 0), nz <= 32768)");
 		}
 		v->nbricks = (size_t)v->g.Dx * rows * chunks;
-		CU_OR_DESTROY(cudaMalloc(&v->d_list_mixed, v->nbricks * 4));
-		CU_OR_DESTROY(cudaMalloc(&v->d_list_free, v->nbricks * 4));
+		for (auto &c : v->ctx) {
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_mixed, v->nbricks * 4));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_free, v->nbricks * 4));
+		}
 	}
 	v->num_sms = prop.multiProcessorCount;
 	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 4));
@@ -935,6 +1002,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 void sfm_destroy(sfm_volume *v) {
 	if (!v) return;
 	cudaSetDevice(v->desc.device);
+	if (v->prep_stream) cudaStreamSynchronize(v->prep_stream);
 	if (v->stream) cudaStreamSynchronize(v->stream);
 	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist); cudaFree(v->planes.occ);
 	if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
@@ -946,8 +1014,15 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->h_stat_ring) cudaFreeHost(v->h_stat_ring);
 	for (int i = 0; i < sfm_volume::kStatRing; i++) if (v->ev_stat[i]) cudaEventDestroy(v->ev_stat[i]);
 	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
-	cudaFree(v->d_tilemax); cudaFree(v->d_depth_m); cudaFree(v->d_stats);
-	cudaFree(v->d_err); cudaFree(v->d_work); cudaFree(v->d_list_mixed); cudaFree(v->d_list_free); cudaFree(v->d_palette); cudaFree(v->d_lut);
+	if (v->prep_stream) cudaStreamDestroy(v->prep_stream);
+	for (auto &c : v->ctx) {
+		cudaFree(c.d_tilemax); cudaFree(c.d_depth_m); cudaFree(c.d_work); cudaFree(c.d_list_mixed); cudaFree(c.d_list_free);
+		if (c.ev_ready) cudaEventDestroy(c.ev_ready);
+		if (c.ev_free) cudaEventDestroy(c.ev_free);
+	}
+	if (v->ev_call) cudaEventDestroy(v->ev_call);
+	cudaFree(v->d_stats);
+	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);
 	for (int i = 0; i < 2; i++) {
@@ -965,6 +1040,7 @@ void sfm_destroy(sfm_volume *v) {
 	for (int i = 0; i < sfm_volume::kRing; i++) {
 		if (v->ev_k0[i]) cudaEventDestroy(v->ev_k0[i]);
 		if (v->ev_km[i]) cudaEventDestroy(v->ev_km[i]);
+		if (v->ev_kb[i]) cudaEventDestroy(v->ev_kb[i]);
 		if (v->ev_k1[i]) cudaEventDestroy(v->ev_k1[i]);
 	}
 	if (v->own_stream && v->stream) cudaStreamDestroy(v->stream);
@@ -1032,13 +1108,23 @@ int sfm_integrate_dev(sfm_volume *v, const void *d_depth, const void *d_color, c
 	return integrate_device(v, d_depth, d_color, d_mask, E16);
 }
 
+int sfm_integrate_dev_ready(sfm_volume *v, const void *d_depth, const void *d_color, const void *d_mask, const float *E16, void *ready_event) {
+	if (!v || !d_depth || !d_color || !E16 || (v->bins > 0 && !d_mask)) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = enqueue_prepare(v, d_depth, d_color, d_mask, E16, ready_event ? (cudaEvent_t)ready_event : kReadyNow);
+	if (rc) return rc;
+	// K1b reads the colour / label images on the main stream: it must see them too
+	if (ready_event) CU(cudaStreamWaitEvent(v->stream, (cudaEvent_t)ready_event, 0));
+	return enqueue_update(v, d_depth, d_color, d_mask, E16);
+}
+
 int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask, const float *E16) {
 	if (!v || !depth || !color || !E16 || (v->bins > 0 && !mask)) return fail(SFM_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(v->desc.device));
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
 	int rc = upload_frame(v, depth, color, v->bins > 0 ? mask : nullptr);
 	if (rc) return rc;
-	rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+	rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
 	if (rc) return rc;
 	return release_frame(v);
 }
@@ -1102,11 +1188,16 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 			// everything up to the integration is enqueued without a host round trip: march, fold, decision
 			// and relabel on the device; the host only waits for the 2 KB report to relabel ITS copy of the
 			// mask, which overlaps the integrate kernels
+			// (K0 + K1a of this frame run on prep_stream meanwhile: they only need the uploaded images; the
+			// relabel waits for them because K0 range-checks the incoming labels)
+			rc = enqueue_prepare(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
+			if (rc) return rc;
 			rc = enqueue_march_fold(v, E16, v->d_mask);
 			if (rc) return rc;
+			CU(cudaStreamWaitEvent(v->stream, v->ctx[v->n_integrate % sfm_volume::kCtx].ev_ready, 0));
 			rc = enqueue_device_decision(v, v->d_fold, v->d_mask);
 			if (rc) return rc;
-			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+			rc = enqueue_update(v, v->d_depth, v->d_rgb, v->d_mask, E16);
 			if (rc) return rc;
 			uint8_t lut[256];
 			rc = finish_device_decision(v, lut);
@@ -1114,13 +1205,13 @@ int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, u
 			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // tsdf.cu:372-389 does it in place
 		} else {
 			v->num_objs = mx + 1;  // tsdf.cu:464-467
-			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
 			if (rc) return rc;
 		}
 	} else {
 		rc = upload_frame(v, depth, color, nullptr);
 		if (rc) return rc;
-		rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16);
+		rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
 		if (rc) return rc;
 	}
 	return release_frame(v);
@@ -1458,7 +1549,10 @@ int sfm_integrate_times(sfm_volume *v, float *ms, int n) {
 	for (int i = 0; i < n; i++) {
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
-		CU(cudaEventElapsedTime(ms + i, v->ev_k0[slot], v->ev_k1[slot]));
+		float a = 0.f, b = 0.f;  // K1a (prep_stream) + K1b (main stream): the two may overlap other frames' kernels
+		CU(cudaEventElapsedTime(&a, v->ev_k0[slot], v->ev_km[slot]));
+		CU(cudaEventElapsedTime(&b, v->ev_kb[slot], v->ev_k1[slot]));
+		ms[i] = a + b;
 	}
 	return SFM_OK;
 }
@@ -1472,7 +1566,7 @@ int sfm_integrate_times2(sfm_volume *v, float *ms_classify, float *ms_update, in
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
 		CU(cudaEventElapsedTime(ms_classify + i, v->ev_k0[slot], v->ev_km[slot]));
-		CU(cudaEventElapsedTime(ms_update + i, v->ev_km[slot], v->ev_k1[slot]));
+		CU(cudaEventElapsedTime(ms_update + i, v->ev_kb[slot], v->ev_k1[slot]));
 	}
 	return SFM_OK;
 }

@@ -109,10 +109,20 @@ class Volume:
         mask = self._img(mask, np.uint8, 1) if mask is not None else None
         check(self.lib.sfm_integrate_raw(self._h, _ptr(depth), _ptr(color), _ptr(mask), _ptr(_f32(extrinsic2init, 16))))
 
-    def integrate_dev(self, d_depth, d_color, d_mask, extrinsic2init):
-        """Frame images given as device pointers (ints), e.g. torch tensors' data_ptr()."""
-        check(self.lib.sfm_integrate_dev(self._h, C.c_void_p(d_depth), C.c_void_p(d_color),
-                                         C.c_void_p(d_mask) if d_mask else None, _ptr(_f32(extrinsic2init, 16))))
+    READY_IN_ORDER = object()
+
+    def integrate_dev(self, d_depth, d_color, d_mask, extrinsic2init, ready=READY_IN_ORDER):
+        """Frame images given as device pointers (ints), e.g. torch tensors' data_ptr().
+        `ready`: when the images are valid -- READY_IN_ORDER (default: in the order of the handle's stream),
+        None (valid already) or a cudaEvent_t handle / torch.cuda.Event the producer recorded; the last two
+        let the frame preparation (K0 + K1a) overlap the previous frame's update kernel."""
+        m = C.c_void_p(d_mask) if d_mask else None
+        if ready is Volume.READY_IN_ORDER:
+            check(self.lib.sfm_integrate_dev(self._h, C.c_void_p(d_depth), C.c_void_p(d_color), m, _ptr(_f32(extrinsic2init, 16))))
+            return
+        ev = getattr(ready, "cuda_event", ready)  # torch.cuda.Event -> raw handle
+        check(self.lib.sfm_integrate_dev_ready(self._h, C.c_void_p(d_depth), C.c_void_p(d_color), m, _ptr(_f32(extrinsic2init, 16)),
+                                               C.c_void_p(ev) if ev else None))
 
     def fuse_frame(self, depth, color, mask_inout, extrinsic2init):
         depth, color = self._img(depth, np.uint16, 1), self._img(color, np.uint8, 3)
