@@ -23,11 +23,10 @@
 //     1.0f; an SDF quad whose bits did not change is not written back.
 //   * Per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
 //     shuffles + one spread atomic pair per warp -- they define the algorithmic bytes of the step.
-//   * Super-blocks: the unit a warp fetches is a box of kSbX x-planes x kSbG brick rows x one 32-z
-//     chunk (= 32 bricks, one per lane).  Before stage A the whole warp classifies the BOX with the
-//     same conservative test (8 corners on 8 lanes, CREDUX.F32 min/max, lane-strided tile scan):
-//     about 70 % of the boxes of a 512^3 volume are CULL and cost ~100 warp instructions instead of
-//     a full stage A; a FREE box skips the per-brick classification as well.
+//   * Super-blocks: a box of kSbX x-planes x kSbG brick rows x one z chunk (= 32 bricks).  K1a first
+//     classifies whole BOXES, one thread each, with the same conservative test; about half the boxes of
+//     a 512^3 frame are CULL there and never reach the per-brick classification (one warp per surviving
+//     box, one brick per lane); a FREE box skips it as well.
 #pragma once
 #include "sfm_device.cuh"
 
@@ -137,18 +136,6 @@ constexpr int kK1Threads = SFM_K1_THREADS;
 
 constexpr int kSbX = 8;  // super-block: kSbX x-planes x kSbG brick rows x one 32-z chunk = 32 bricks
 constexpr int kSbG = 4;
-
-// warp-wide float min / max in one instruction (sm_100a: redux.sync.f32 -> CREDUX); NaNs are ignored
-__device__ __forceinline__ float redux_min(float v) {
-	float r;
-	asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-	return r;
-}
-__device__ __forceinline__ float redux_max(float v) {
-	float r;
-	asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-	return r;
-}
 
 // s = K[0:3,0:3] * c in the reference's compiled order (tsdf.cu:35-37 -> dot3_ref).  KCANON: the
 // intrinsic matrix has the pinhole pattern [[fx,0,cx],[0,fy,cy],[0,0,1]] (kernel.cpp:39-40,
@@ -312,24 +299,28 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 	return classify_bounds<false>(f, g, tilemax, tilemin, b, 0, 96);
 }
 
-// Whole-warp classification of a super-block: lanes 0..7 (and their copies) project the 8 corners.
-__device__ __forceinline__ int classify_superblock(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
-	const uint16_t *tilemin, int x0, int x1, int y0, int y1, int zc0, int zc1, int lane)
+// One lane classifies a whole box (8 corners): the super-block pre-pass of K1a.
+__device__ __forceinline__ int classify_box_lane(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
+	const uint16_t *tilemin, int x0, int x1, int y0, int y1, int zc0, int zc1)
 {
-	const float px = __fmaf_rn((float)((lane & 1) ? x1 : x0), g.vx, g.sx);
-	const float py = __fmaf_rn((float)((lane & 2) ? y1 : y0), g.vy, g.sy);
-	const float pz = __fmaf_rn((float)(g.z0 + ((lane & 4) ? zc1 : zc0)), g.vz, g.sz);
-	float u, v, sz, cz, scale;
-	project_corner(f, px, py, pz, u, v, sz, cz, scale);
-	const bool finite = fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
-	if (!__all_sync(0xffffffffu, finite)) return kMixed;
-	BoxBounds b;
-	b.umin = redux_min(u); b.umax = redux_max(u);
-	b.vmin = redux_min(v); b.vmax = redux_max(v);
-	b.szmin = redux_min(sz); b.szmax = redux_max(sz);
-	b.czmin = redux_min(cz); b.czmax = redux_max(cz);
-	b.scale_c = redux_max(scale);
-	return classify_bounds<true>(f, g, tilemax, tilemin, b, lane, 1024);
+	BoxBounds b{INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY, 0.f};
+	bool finite = true;
+#pragma unroll 2
+	for (int corner = 0; corner < 8; corner++) {
+		const float px = __fmaf_rn((float)((corner & 1) ? x1 : x0), g.vx, g.sx);
+		const float py = __fmaf_rn((float)((corner & 2) ? y1 : y0), g.vy, g.sy);
+		const float pz = __fmaf_rn((float)(g.z0 + ((corner & 4) ? zc1 : zc0)), g.vz, g.sz);
+		float u, v, sz, cz, scale;
+		project_corner(f, px, py, pz, u, v, sz, cz, scale);
+		b.umin = fminf(b.umin, u); b.umax = fmaxf(b.umax, u);
+		b.vmin = fminf(b.vmin, v); b.vmax = fmaxf(b.vmax, v);
+		b.szmin = fminf(b.szmin, sz); b.szmax = fmaxf(b.szmax, sz);
+		b.czmin = fminf(b.czmin, cz); b.czmax = fmaxf(b.czmax, cz);
+		b.scale_c = fmaxf(b.scale_c, scale);
+		finite &= fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
+	}
+	if (!finite) return kMixed;
+	return classify_bounds<false>(f, g, tilemax, tilemin, b, 0, 160);
 }
 
 // Brick work lists written by K1a and consumed by K1b.  A brick id packs (x, brick row, z chunk).
@@ -403,29 +394,46 @@ __global__ void __launch_bounds__(kK1aThreads) classify_kernel(VolGeom g, FrameV
 	uint32_t *s_mixed = reinterpret_cast<uint32_t *>(smem_dyn + (TMA_TILES ? f.tile_bytes : 0));
 	uint32_t *s_free = s_mixed + kSbPerBlock * 32;
 	// The block owns the super-blocks blockIdx.x + k * gridDim.x (a sample of the whole volume, so every
-	// block gets about the same mix of culled and surviving boxes); its warps pull k from a shared
-	// counter, so a warp that lands on culled boxes takes more of them.
-	__shared__ unsigned s_next;
+	// block gets about the same mix of culled and surviving boxes).
+	// Pass 1, one THREAD per super-block: the box test (8 corners, tiles under the bounding box).  About half
+	// the boxes of a frame are culled here for ~25 warp instructions each (a whole warp per box costs 170),
+	// and a rank whose slab lies behind the surfaces is done after this pass.  Survivors go to a queue.
+	// Pass 2, one WARP per surviving super-block, pulled from the queue: one brick per lane.
+	__shared__ unsigned s_queue[kSbPerBlock], s_qn, s_qhead;
 	if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-	if (threadIdx.x == 2) s_next = 0;
+	if (threadIdx.x == 2) s_qn = 0;
+	if (threadIdx.x == 3) s_qhead = 0;
 	__syncthreads();
-	for (;;) {
-		unsigned k = 0;
-		if (lane == 0) k = atomicAdd(&s_next, 1u);
-		k = __shfl_sync(0xffffffffu, k, 0);
+	auto sb_box = [&](unsigned sb, int &x0, int &gy0, int &sbz, int &zc0, int &zc1) {  // z chunk fastest
+		sbz = (int)(sb % (unsigned)nchunks);
+		const unsigned sbt = sb / (unsigned)nchunks;
+		gy0 = (int)(sbt % (unsigned)nsby) * kSbG;
+		x0 = (int)(sbt / (unsigned)nsby) * kSbX;
+		zc0 = sbz << csh;
+		zc1 = min(zc0 + (1 << csh) - 1, g.nz - 1);
+	};
+	for (unsigned k = threadIdx.x;; k += blockDim.x) {
 		const unsigned long long sb64 = (unsigned long long)blockIdx.x + (unsigned long long)k * gridDim.x;
 		if (sb64 >= nsb) break;
-		const unsigned sb = (unsigned)sb64;
-		// super-block -> box (z chunk fastest)
-		const int sbz = (int)(sb % (unsigned)nchunks);
-		const unsigned sbt = sb / (unsigned)nchunks;
-		const int gy0 = (int)(sbt % (unsigned)nsby) * kSbG, x0 = (int)(sbt / (unsigned)nsby) * kSbX;
-		const int zc0 = sbz << csh, zc1 = min(zc0 + (1 << csh) - 1, g.nz - 1);
+		int x0, gy0, sbz, zc0, zc1;
+		sb_box((unsigned)sb64, x0, gy0, sbz, zc0, zc1);
 		int sbcls = kMixed;
 		if (CULL && !(f.debug & 8))
-			sbcls = classify_superblock(f, g, s_tilemax, s_tilemin, x0, min(x0 + kSbX - 1, g.Dx - 1), gy0 * CPW,
-				min((gy0 + kSbG) * CPW - 1, g.Dy - 1), zc0, zc1, lane);
-		if (sbcls == kCull) continue;
+			sbcls = classify_box_lane(f, g, s_tilemax, s_tilemin, x0, min(x0 + kSbX - 1, g.Dx - 1), gy0 * CPW,
+				min((gy0 + kSbG) * CPW - 1, g.Dy - 1), zc0, zc1);
+		if (sbcls != kCull) s_queue[atomicAdd(&s_qn, 1u)] = (unsigned)sb64 | (sbcls == kFree ? 0x80000000u : 0u);
+	}
+	__syncthreads();
+	const unsigned qn = s_qn;
+	for (;;) {
+		unsigned qi = 0;
+		if (lane == 0) qi = atomicAdd(&s_qhead, 1u);
+		qi = __shfl_sync(0xffffffffu, qi, 0);
+		if (qi >= qn) break;
+		const unsigned entry = s_queue[qi];
+		const int sbcls = (entry & 0x80000000u) ? kFree : kMixed;
+		int x0, gy0, sbz, zc0, zc1;
+		sb_box(entry & 0x7fffffffu, x0, gy0, sbz, zc0, zc1);
 		int cls = kCull;
 		const int bx = x0 + (lane >> 2), bg = gy0 + (lane & 3), by0 = bg * CPW;
 		if (bx < g.Dx && by0 < g.Dy)

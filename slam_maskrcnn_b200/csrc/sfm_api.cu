@@ -398,6 +398,7 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 	const int cpw = vec4 ? (32 >> v->g.zl_log2) : 1, chunk = vec4 ? (4 << v->g.zl_log2) : 32;
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
 	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
+	if (nsb >= (1LL << 31)) return fail(SFM_ERR_INVALID, "volume too large for the 31-bit super-block ids");
 	v->g.brick_mul = 1;
 	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
 	CU(cudaEventRecord(v->ev_k0[slot], v->prep_stream));
