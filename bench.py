@@ -294,33 +294,6 @@ def run_ours(args):
         return v
 
     vol = make_volume(plan)
-    # calibration (N > 1): the profile's cost model is approximate, so the plan is refined from measured
-    # per-rank kernel times: a few frames are integrated, the profile inside every slab is rescaled to the
-    # slab's measured time, the slabs are re-planned and the volume re-allocated.  Part of set-up, not timed.
-    calib = []
-    if world > 1 and not args.equal_slabs:
-        for it in range(args.calibrate):
-            for i in range(6):
-                fr = frames[i % n_pool]
-                vol.integrate_raw(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"])
-            vol.synchronize()
-            t_mine = float(vol.integrate_times2(4)[1].mean())  # K1b: the preparation kernels overlap it
-            ts = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
-            dist.all_gather(ts, torch.tensor([t_mine], dtype=torch.float64, device="cuda"))
-            ts = [float(t.item()) for t in ts]
-            calib.append([round(t, 4) for t in ts])
-            profile = slabs_mod.refine_profile(profile, plan, ts)
-            new_plan = slabs_mod.plan_slabs(dims[2], world, profile)
-            if new_plan == plan:
-                break
-            plan = new_plan
-            vol.close()
-            vol = make_volume(plan)
-        # start the measurement from a clean volume
-        vol.close()
-        vol = make_volume(plan)
-    slab = plan[rank]
-    nz = slab[1]
 
     # frames: packed [depth | colour | mask | pose] byte buffers, pinned on the host and resident in HBM
     npx = 640 * 480
@@ -338,37 +311,46 @@ def run_ours(args):
         packed_dev = [b.cuda(non_blocking=True) for b in packed_host]
     else:
         packed_dev = None
-    bcast_buf = [torch.empty(FRAME_BYTES + POSE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    # N > 1: frames are fetched ahead in groups of GROUP (rank 0: copies into a broadcast buffer; all: ONE
+    # ncclBroadcast per group) on a side stream while earlier frames integrate.  NCCL's kernel cannot run next
+    # to a resident wave of K1b (no SM has room for its thread blocks), so every broadcast costs a ~15 us gap
+    # between two K1b launches whatever it carries: grouping frames pays that once per GROUP steps.
+    NBUF, GROUP = 3, 4
+    FB = FRAME_BYTES + POSE_BYTES
+    bcast_buf = [torch.empty(GROUP * FB, dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
     torch.cuda.synchronize()
-
-    # N > 1: the frame of step i+1 is fetched (rank 0: copy into the broadcast buffer; all: ncclBroadcast)
-    # on a side stream while step i integrates; two buffers, events in both directions.
     main_stream = torch.cuda.current_stream()
     side_stream = torch.cuda.Stream() if world > 1 else None
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-    fetched = {"next": None}
+    ev_ready = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_free = [torch.cuda.Event() for _ in range(NBUF)]
+    fetched = {"upto": -1, "mode": None}
 
-    def fetch(i, from_host):
-        b, j = i & 1, i % n_pool
+    def fetch(gi, from_host):
+        """group gi = frames gi*GROUP .. gi*GROUP+GROUP-1"""
+        b = gi % NBUF
         with torch.cuda.stream(side_stream):
-            side_stream.wait_event(ev_free[b])  # the integrate that read this buffer has finished
+            side_stream.wait_event(ev_free[b])  # the integrates that read this buffer have finished
             if rank == 0:
-                bcast_buf[b].copy_(packed_host[j] if from_host else packed_dev[j], non_blocking=True)
+                for k in range(GROUP):
+                    j = (gi * GROUP + k) % n_pool
+                    bcast_buf[b][k * FB:(k + 1) * FB].copy_(packed_host[j] if from_host else packed_dev[j], non_blocking=True)
             dist.broadcast(bcast_buf[b], src=0)
             ev_ready[b].record(side_stream)
 
     def step_sharded(i, from_host):
-        if fetched["next"] != i:
-            fetch(i, from_host)
-        fetch(i + 1, from_host)
-        fetched["next"] = i + 1
-        b, j = i & 1, i % n_pool
-        p = bcast_buf[b].data_ptr()
+        gi, k = i // GROUP, i % GROUP
+        if fetched["mode"] != from_host or fetched["upto"] < gi - 1 or fetched["upto"] > gi + NBUF - 1:
+            fetched["upto"], fetched["mode"] = gi - 1, from_host  # (re)start the look-ahead at this group
+        while fetched["upto"] < gi + NBUF - 2:
+            fetched["upto"] += 1
+            fetch(fetched["upto"], from_host)
+        b, j = gi % NBUF, i % n_pool
+        p = bcast_buf[b].data_ptr() + k * FB
         # the broadcast's event tells the library when the frame is valid: K0 + K1a of this frame then run on
         # its preparation stream next to the previous frame's K1b
         vol.integrate_dev(p, p + npx * 2, p + npx * 5, poses[j], ready=ev_ready[b])
-        ev_free[b].record(main_stream)
+        if k == GROUP - 1:
+            ev_free[b].record(main_stream)
 
     def step_device(i):
         """One step with the frame resident in (rank 0's) HBM."""
@@ -392,6 +374,39 @@ def run_ours(args):
         e2e_state["ticket"] = ticket
         if prev is not None:
             e2e_state["totals"] = vol.stats_end(prev)
+
+    # calibration (N > 1): the profile's cost model is approximate, so the plan is refined from measured
+    # per-rank K1b times taken through the SAME path the timed loop uses (grouped broadcast + sharded steps):
+    # the profile inside every slab is rescaled to the slab's measured time, the slabs are re-planned and the
+    # volume re-allocated.  Part of set-up, not timed.
+    calib = []
+    if world > 1 and not args.equal_slabs:
+        for it in range(args.calibrate):
+            fetched["upto"], fetched["mode"] = -1, None
+            for i in range(3 * GROUP):
+                step_sharded(i, False)
+            vol.synchronize()
+            torch.cuda.synchronize()
+            t_mine = float(vol.integrate_times2(2 * GROUP)[1].mean())  # K1b: the preparation kernels overlap it
+            ts = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(ts, torch.tensor([t_mine], dtype=torch.float64, device="cuda"))
+            ts = [float(t.item()) for t in ts]
+            calib.append([round(t, 4) for t in ts])
+            profile = slabs_mod.refine_profile(profile, plan, ts)
+            new_plan = slabs_mod.plan_slabs(dims[2], world, profile)
+            if new_plan == plan:
+                break
+            plan = new_plan
+            vol.close()
+            vol = make_volume(plan)
+        # start the measurement from a clean volume
+        vol.close()
+        vol = make_volume(plan)
+        fetched["upto"], fetched["mode"] = -1, None
+        torch.cuda.synchronize()
+        dist.barrier()
+    slab = plan[rank]
+    nz = slab[1]
 
     e2e_state = {}
 
@@ -462,7 +477,7 @@ def run_ours(args):
         iso = {"classify_kernel_ms": float(a_iso[4:].mean()), "kernel_ms": float(b_iso[4:].mean())}
 
     # ---- end-to-end region (host buffers, H2D + result D2H every step) ----------------------
-    fetched["next"] = None
+    fetched["upto"], fetched["mode"] = -1, None
     for i in range(3):
         step_e2e(i)
     barrier()
@@ -569,7 +584,7 @@ def run_ours(args):
                        "invalid_depth_model": args.hole_model + (" (15 % invalid pixels, spatially clustered like the TUM fr2 frames the reference ships)"
                                                                  if args.hole_model == "tum" else " (15 % independent per-pixel holes)"),
                        "l2": "no flush: each step reads and writes ~0.25 GB of voxel planes out of a >40 GB working set (> 126 MB L2)",
-                       "frames_resident": "HBM (rank 0); ncclBroadcast of frame i+1 on a side stream while frame i integrates" if world > 1 else "HBM"},
+                       "frames_resident": "HBM (rank 0); one ncclBroadcast per group of 4 frames on a side stream, one group ahead of the frames being integrated" if world > 1 else "HBM"},
             "touched_voxel_updates_per_s": U_all / (t_dev_ms * 1e-3),
             "U_per_step": U_all / K_steps, "S_per_step": S_all / K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -696,13 +696,14 @@ __global__ void __launch_bounds__(256) decide_kernel(FoldTables tb, int L, float
 {
 	__shared__ int s_best[256];
 	__shared__ float s_bp[256], s_second[256];
+	__shared__ unsigned s_first[256], s_cm[256];  // staged in parallel: thread 0's loops below must not chase global loads
 	__shared__ int s_max_obj;
 	const int m = threadIdx.x;
-	if (m == 0) {
-		int mx = 0;
-		for (int k = 1; k < L; k++) if (tb.Cm[k]) mx = k;
-		s_max_obj = mx + 1;
-	}
+	s_first[m] = m < L ? tb.FirstPix[m] : 0xffffffffu;
+	s_cm[m] = m < L ? tb.Cm[m] : 0u;
+	if (m == 0) s_max_obj = 1;
+	__syncthreads();
+	if (m >= 1 && m < L && s_cm[m]) atomicMax(&s_max_obj, m + 1);
 	__syncthreads();
 	const int max_obj_now = s_max_obj;
 	int best = -1;
@@ -717,52 +718,54 @@ __global__ void __launch_bounds__(256) decide_kernel(FoldTables tb, int L, float
 			else if (p > second) second = p;
 		}
 	}
+	__shared__ int s_owner[256], s_assign[256], s_newmax;
+	__shared__ float s_owner_p[256];
 	s_best[m] = best; s_bp[m] = bp; s_second[m] = second;
-	__syncthreads();
-	if (m != 0) return;
+	s_owner[m] = 0; s_owner_p[m] = 0.f; s_assign[m] = 0;
+	if (m == 0) s_newmax = 0;
 	sfm_merge_report &rep = out->rep;
-	const float thr = accept_factor * prior;
-	float margin = INFINITY;
-	int owner[256];
-	float owner_p[256];
-	for (int k = 0; k < 256; k++) { owner[k] = 0; owner_p[k] = 0.f; rep.assign[k] = 0; rep.best_prob[k] = 0.f; }
-	rep.max_obj_now = max_obj_now;
-	for (int k = 1; k < max_obj_now && k < L; k++) {
-		const float kbp = s_bp[k];
-		const int kb = s_best[k];
-		rep.best_prob[k] = kbp;
-		if (tb.FirstPix[k] != 0xffffffffu) {  // only labels present in the frame decide anything visible
-			margin = fminf(margin, fabsf(kbp - thr));
-			if (kbp > thr) margin = fminf(margin, kbp - s_second[k]);
-		}
-		if (kbp > thr) {
-			if (owner[kb] == 0) { owner[kb] = k; owner_p[kb] = kbp; }
-			else {
-				margin = fminf(margin, fabsf(owner_p[kb] - kbp));
-				if (owner_p[kb] < kbp) { owner[kb] = k; owner_p[kb] = kbp; }
+	rep.best_prob[m] = (m >= 1 && m < max_obj_now && m < L) ? bp : 0.f;
+	__syncthreads();
+	if (m == 0) {  // the sequential parts, on shared memory only
+		const float thr = accept_factor * prior;
+		float margin = INFINITY;
+		for (int k = 1; k < max_obj_now && k < L; k++) {
+			const float kbp = s_bp[k];
+			const int kb = s_best[k];
+			if (s_first[k] != 0xffffffffu) {  // only labels present in the frame decide anything visible
+				margin = fminf(margin, fabsf(kbp - thr));
+				if (kbp > thr) margin = fminf(margin, kbp - s_second[k]);
+			}
+			if (kbp > thr) {
+				if (s_owner[kb] == 0) { s_owner[kb] = k; s_owner_p[kb] = kbp; }
+				else {
+					margin = fminf(margin, fabsf(s_owner_p[kb] - kbp));
+					if (s_owner_p[kb] < kbp) { s_owner[kb] = k; s_owner_p[kb] = kbp; }
+				}
 			}
 		}
+		for (int j = 1; j < 256; j++) if (s_owner[j]) s_assign[s_owner[j]] = j;
+		// unassigned labels that occur get fresh ids in raster order of first appearance: repeated selection of
+		// the smallest first-pixel index among them (at most 255 labels)
+		int num_objs = num_objs_in;
+		for (;;) {
+			unsigned bestpix = 0xffffffffu;
+			int bestm = 0;
+			for (int k = 1; k < max_obj_now && k < L; k++)
+				if (!s_assign[k] && s_first[k] < bestpix) { bestpix = s_first[k]; bestm = k; }
+			if (!bestm) break;
+			s_assign[bestm] = num_objs++;
+		}
+		rep.max_obj_now = max_obj_now;
+		rep.num_objs = num_objs;
+		rep.margin = margin;
 	}
-	for (int j = 1; j < 256; j++) if (owner[j]) rep.assign[owner[j]] = j;
-	// unassigned labels that occur get fresh ids in raster order of first appearance: repeated selection of
-	// the smallest first-pixel index among them (at most 255 labels)
-	int num_objs = num_objs_in;
-	for (;;) {
-		unsigned bestpix = 0xffffffffu;
-		int bestm = 0;
-		for (int k = 1; k < max_obj_now && k < L; k++)
-			if (!rep.assign[k] && tb.FirstPix[k] < bestpix) { bestpix = tb.FirstPix[k]; bestm = k; }
-		if (!bestm) break;
-		rep.assign[bestm] = num_objs++;
-	}
-	rep.num_objs = num_objs;
-	rep.margin = margin;
-	int newmax = 0;
-	for (int k = 0; k < 256; k++) {
-		out->lut[k] = (uint8_t)rep.assign[k];
-		if (k < max_obj_now) newmax = max(newmax, rep.assign[k]);
-	}
-	out->overflow = newmax >= L ? 1 : 0;
+	__syncthreads();
+	rep.assign[m] = s_assign[m];
+	out->lut[m] = (uint8_t)s_assign[m];
+	if (m < max_obj_now) atomicMax(&s_newmax, s_assign[m]);
+	__syncthreads();
+	if (m == 0) out->overflow = s_newmax >= L ? 1 : 0;
 }
 
 static_assert(sizeof(MergeOut) <= 4096, "MergeOut buffer");
