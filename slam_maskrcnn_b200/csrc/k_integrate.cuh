@@ -1,12 +1,12 @@
-// k_integrate.cuh -- K0 (frame prep) and K1 (TSDF integrate) for sm_100a.
+// k_integrate.cuh -- K0 (frame prep), K1a (brick classification) and K1b (TSDF update) for sm_100a.
 //
-// K1 replaces tsdf_kernel (reference src/SfM_CUDA/tsdf.cu:18-70).  Design, B200-first:
+// K1a + K1b replace tsdf_kernel (reference src/SfM_CUDA/tsdf.cu:18-70).  Design, B200-first:
 //
-//   * Work item = brick: CPW columns (consecutive y) x 32 consecutive z voxels at one x.  In the
-//     reference layout (z fastest) a brick is CPW full 128 B lines of each plane.
-//   * Stage A (classify): each of the 32 lanes of a warp classifies ONE brick by projecting its
-//     4 corners and querying two per-frame 8x8-pixel tile grids (max depth, min depth with
-//     invalid = 0) built by K0:
+//   * Work item = brick: CPW columns (consecutive y) x 32 consecutive z voxels at one x (thin z-slabs use
+//     flatter bricks, VolGeom::zl_log2).  In the reference layout (z fastest) a brick is CPW full 128 B
+//     lines of each plane.
+//   * K1a (classify_kernel) sorts bricks into three classes with two per-frame 8x8-pixel tile grids (max
+//     depth, min depth with invalid = 0) built by K0:
 //        CULL   every voxel provably fails the reference's own tests (outside the image, only
 //               invalid depth under it, or behind the surface band: cz - depth >= miu);
 //        FREE   every voxel provably lands inside the image on a valid pixel and in front of the
@@ -14,8 +14,11 @@
 //               for all of them: no per-voxel projection is needed at all;
 //        MIXED  anything else: per-voxel evaluation, bit-identical to the reference.
 //     The tests are conservative with an explicit rounding-error budget, so results never change
-//     (SFM_FLAG_NO_CULL forces every brick to MIXED; the parity tests compare both).
-//   * Stage B (update): the warp walks the non-CULL bricks found by two ballots.  One lane owns
+//     (SFM_FLAG_NO_CULL lists every brick as MIXED; the parity tests compare both).  Whole boxes of 32
+//     bricks (super-blocks: kSbX x-planes x kSbG brick rows x one z chunk) are tested first, one THREAD
+//     per box: about half the boxes of a 512^3 frame are CULL there; then one WARP per surviving box, one
+//     brick per lane.  Surviving bricks go to a MIXED and a FREE list in global memory.
+//   * K1b (integrate_kernel) is a persistent grid whose warps pull bricks from the lists.  One lane owns
 //     VEC=4 consecutive z voxels of one column: SDF / weight move as 128-bit loads and stores, a
 //     warp request is CPW full lines.  The z-invariant part of the pose transform
 //     (fma(px,r0,py*r1), the order the reference's SASS uses) is hoisted per column.
@@ -23,10 +26,8 @@
 //     1.0f; an SDF quad whose bits did not change is not written back.
 //   * Per-frame U (weight increments) and S (histogram/colour updates) are folded with warp
 //     shuffles + one spread atomic pair per warp -- they define the algorithmic bytes of the step.
-//   * Super-blocks: a box of kSbX x-planes x kSbG brick rows x one z chunk (= 32 bricks).  K1a first
-//     classifies whole BOXES, one thread each, with the same conservative test; about half the boxes of
-//     a 512^3 frame are CULL there and never reach the per-brick classification (one warp per surviving
-//     box, one brick per lane); a FREE box skips it as well.
+//   * K0 and K1a never touch the volume: the host runs them on a second stream, one frame ahead of K1b
+//     (sfm_api.cu: enqueue_prepare / enqueue_update).
 #pragma once
 #include "sfm_device.cuh"
 
@@ -36,7 +37,7 @@ namespace sfm {
 // K0: per-frame prep.  One warp per kTile x kTile tile: max depth, min depth (invalid pixels
 // count as 0, so min > 0 <=> the tile has no hole), depth in metres as f32 (the reference's
 // depth/5000.f, IEEE divide, tsdf.cu:49) and max label (labels >= bins are a contract violation,
-// SURVEY appendix B.2).  Also resets K1's dynamic work counter.
+// SURVEY appendix B.2).  Also resets K1's list counters and fetch cursor.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restrict__ depth,
 	const uint8_t *__restrict__ mask, int W, int H, int TW, int TH, int bins, float depth_scale,
@@ -203,8 +204,7 @@ struct BoxBounds {
 	float umin, umax, vmin, vmax, szmin, szmax, czmin, czmax, scale_c;
 };
 
-// Second half of the conservative classification, shared by bricks (one lane each, COOP = false)
-// and super-blocks (whole warp, COOP = true: the tiles under the box are scanned lane-strided).
+// Second half of the conservative classification, shared by bricks and super-blocks (one lane each).
 // The projective map sends segments that stay on one side of the camera plane to segments, so with
 // all corners of a (convex) box strictly on one side the pixel coordinates of every voxel of the box
 // lie inside the bounding box of the projected corners (plus rounding slack), and the camera-space
@@ -212,9 +212,8 @@ struct BoxBounds {
 // per-voxel error of c*, s* ~ 1e-6*scale; a box is only classified when all corners are at least
 // 1e-2*scale_sz away from the camera plane, which bounds the per-voxel pixel error by
 // ~1e-4*(Krow/K2row + |u|) -- the slack is 10x that.
-template <bool COOP>
 __device__ __forceinline__ int classify_bounds(const FrameView &f, const VolGeom &g, const uint16_t *tilemax,
-	const uint16_t *tilemin, const BoxBounds &b, int lane, int max_tiles)
+	const uint16_t *tilemin, const BoxBounds &b, int max_tiles)
 {
 	const float zguard = 1e-2f * f.cull_k2 * b.scale_c;
 	const bool one_side = (b.szmin > zguard) || (b.szmax < -zguard);
@@ -230,21 +229,11 @@ __device__ __forceinline__ int classify_bounds(const FrameView &f, const VolGeom
 	const int tw = tx1 - tx0 + 1, nt = tw * (ty1 - ty0 + 1);
 	if (nt > max_tiles) return kMixed;  // huge footprint (box close to the camera)
 	unsigned dmax = 0, dmin = 0xffffu;
-	if (COOP) {
-		for (int i = lane; i < nt; i += 32) {
-			const int r = i / tw, t = (ty0 + r) * f.TW + tx0 + (i - r * tw);
-			dmax = max(dmax, (unsigned)tilemax[t]);
-			dmin = min(dmin, (unsigned)tilemin[t]);
+	for (int ty = ty0; ty <= ty1; ty++)
+		for (int tx = tx0; tx <= tx1; tx++) {
+			dmax = max(dmax, (unsigned)tilemax[ty * f.TW + tx]);
+			dmin = min(dmin, (unsigned)tilemin[ty * f.TW + tx]);
 		}
-		dmax = __reduce_max_sync(0xffffffffu, dmax);
-		dmin = __reduce_min_sync(0xffffffffu, dmin);
-	} else {
-		for (int ty = ty0; ty <= ty1; ty++)
-			for (int tx = tx0; tx <= tx1; tx++) {
-				dmax = max(dmax, (unsigned)tilemax[ty * f.TW + tx]);
-				dmin = min(dmin, (unsigned)tilemin[ty * f.TW + tx]);
-			}
-	}
 	if (dmax == 0) return kCull;  // only invalid depth under the box
 	if (b.szmin > 0.f) {
 		const float dmax_m = __fdiv_rn((float)dmax, f.depth_scale), dmin_m = __fdiv_rn((float)dmin, f.depth_scale);
@@ -296,7 +285,7 @@ __device__ __forceinline__ int classify_brick(const FrameView &f, const VolGeom 
 		finite &= fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
 	}
 	if (!finite) return kMixed;
-	return classify_bounds<false>(f, g, tilemax, tilemin, b, 0, 96);
+	return classify_bounds(f, g, tilemax, tilemin, b, 96);
 }
 
 // One lane classifies a whole box (8 corners): the super-block pre-pass of K1a.
@@ -320,7 +309,7 @@ __device__ __forceinline__ int classify_box_lane(const FrameView &f, const VolGe
 		finite &= fabsf(u) < 1e8f && fabsf(v) < 1e8f && fabsf(cz) < 1e30f;  // NaNs fail
 	}
 	if (!finite) return kMixed;
-	return classify_bounds<false>(f, g, tilemax, tilemin, b, 0, 160);
+	return classify_bounds(f, g, tilemax, tilemin, b, 160);
 }
 
 // Brick work lists written by K1a and consumed by K1b.  A brick id packs (x, brick row, z chunk).
@@ -337,9 +326,7 @@ constexpr int kFetch = SFM_K1_FETCH;           // bricks a K1b warp takes per fe
 #ifndef SFM_K1_PERMUTE
 #define SFM_K1_PERMUTE 1
 #endif
-#ifndef SFM_K1_PIPE
-#define SFM_K1_PIPE 0
-#endif
+
 constexpr int kK1aThreads = 128;               // K1a block size: small enough to run next to a resident wave of K1b
 constexpr int kSbPerBlock = 64;                // most super-blocks one K1a block classifies (sizes its shared lists)
 
@@ -547,13 +534,6 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
 	if (n > 1) prefetch_group(my_id, n);
 	while (n > 0) {
-#if SFM_K1_PIPE
-	// ids of the next group: requested now, needed when the last brick of this group prefetches
-	const unsigned base_n = __shfl_sync(0xffffffffu, next_raw, 0);
-	const int n_n = base_n < total ? (int)min((unsigned)kFetch, total - base_n) : 0;
-	const unsigned id_n = lane < n_n ? list_at(base_n + lane) : 0u;
-	next_raw = fetch();
-#endif
 	for (int i = 0; i < n; i++) {
 		const unsigned id = __shfl_sync(0xffffffffu, my_id, i);
 		const bool is_free = base + i >= nmixed;  // warp-uniform
@@ -565,9 +545,6 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		const size_t v0 = brick_voxel(x, y, zl, ok);
 		// prefetch the next brick
 		if (i + 1 < n) issue(__shfl_sync(0xffffffffu, my_id, i + 1));
-#if SFM_K1_PIPE
-		else if (n_n > 0) issue(__shfl_sync(0xffffffffu, id_n, 0));
-#endif
 		if (f.debug & 1) continue;  // ablation: fetches and loads only
 		F sn = sv;
 		float *sp = reinterpret_cast<float *>(&sn);
@@ -732,16 +709,12 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 			if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 		}
 	}
-#if SFM_K1_PIPE
-	base = base_n; n = n_n; my_id = id_n;
-#else
 	base = __shfl_sync(0xffffffffu, next_raw, 0);
 	n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
 	my_id = lane < n ? list_at(base + lane) : 0u;
 	next_raw = fetch();
 	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
 	if (n > 1) prefetch_group(my_id, n);
-#endif
 	}  // fetch loop
 	if (qcount) nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
 

@@ -316,7 +316,7 @@ void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, lo
 	int blocks = (int)std::max<long long>(std::max(1LL, std::min<long long>((1024LL / kK1aThreads) * v->num_sms, want)), (nsb + kSbPerBlock - 1) / kSbPerBlock);
 	// without the TMA staging a block has no set-up cost: one super-block per warp, and the hardware
 	// block scheduler balances the (very uneven) super-block costs
-	if (!TMA_TILES || getenv("SFM_K1A_WIDE")) blocks = (int)std::max(1LL, want);
+	if (!TMA_TILES) blocks = (int)std::max(1LL, want);
 	kern<<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
 }
 
@@ -399,7 +399,6 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
 	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
 	if (nsb >= (1LL << 31)) return fail(SFM_ERR_INVALID, "volume too large for the 31-bit super-block ids");
-	v->g.brick_mul = 1;
 	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
 	CU(cudaEventRecord(v->ev_k0[slot], v->prep_stream));
 	if (vec4) launch_classify<true>(v, f, wl, nsb);

@@ -25,7 +25,6 @@ struct VolGeom {
 	int oby, obz;         // strides of the 8x8x8 surface-block map (see Planes::occ)
 	int oby2, obz2;       // strides of the coarse 32x32x32 level of the same map
 	unsigned occ2_off;    // byte offset of the coarse level inside the map allocation
-	long long brick_mul;  // (unused since K1b permutes list positions)
 	int zl_log2;  // K1 brick shape on the 128-bit path: 2^zl_log2 lanes (4 voxels each) along z per column, i.e. a
 	              // brick is (32 >> zl_log2) columns x (4 << zl_log2) planes; 3 = 4 columns x 32 planes.  Thin z-slabs
 	              // (a rank that owns only the planes around a fronto-parallel wall) use flatter bricks.
