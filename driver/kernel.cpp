@@ -139,6 +139,7 @@ int main(int argc, char **argv) {
 	string root = ".", render = "render.ppm", render_color, ply;
 	double begin = 68164, end = 68170;  // kernel.cpp:60-61
 	int max_frames = 100, dim = 256, bins = MAX_OBJECTS, views = 10;
+	bool interp = false;  // --interp: lerp + slerp poses (TSDF_Python front-end) instead of the next entry
 	float intr[4] = {520.9f, 521.0f, 325.1f, 249.7f};  // kernel.cpp:39
 	for (int i = 1; i < argc; i++) {
 		const string a = argv[i];
@@ -150,6 +151,7 @@ int main(int argc, char **argv) {
 		else if (a == "--max-frames") max_frames = atoi(next().c_str());
 		else if (a == "--views") views = atoi(next().c_str());
 		else if (a == "--render") render = next();
+		else if (a == "--interp") interp = true;
 		else if (a == "--render-color") render_color = next();
 		else if (a == "--ply") ply = next();
 		else root = a;
@@ -189,7 +191,16 @@ int main(int argc, char **argv) {
 			auto low = traj.lower_bound(depth_ts[i]);  // kernel.cpp:97 (no interpolation)
 			if (low == traj.end()) --low;
 			float extrinsic[16];
-			sfm_parse_extrinsic(low->second.data(), extrinsic);  // kernel.cpp:98
+			if (interp && low != traj.begin() && low->first > depth_ts[i]) {
+				// the TSDF_Python prototype's front-end (main.py:127-138): lerp + slerp between the two entries
+				// that bracket the depth timestamp instead of taking the next one
+				auto prev = std::prev(low);
+				double a8[8] = {prev->first}, b8[8] = {low->first}, pose7[7];
+				for (int k = 0; k < 7; k++) { a8[1 + k] = prev->second[k]; b8[1 + k] = low->second[k]; }
+				sfm_interpolate_pose(a8, b8, depth_ts[i], pose7);
+				sfm_parse_extrinsic(pose7, extrinsic);
+			} else
+				sfm_parse_extrinsic(low->second.data(), extrinsic);  // kernel.cpp:98
 			tsdf->parse_frame(depth_img, rgb_img, mask_img, extrinsic, mean);  // kernel.cpp:99
 		}
 		const sfm_info info = tsdf->info();

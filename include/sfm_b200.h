@@ -269,6 +269,11 @@ int sfm_debug_divcheck(float b, unsigned seed, int blocks, int per_thread, float
 float sfm_mean_depth(const uint16_t *depth, int n);
 /* parse_extrinsic (utils.cu:8-24): pose {tx,ty,tz,qx,qy,qz,qw} -> world->camera 4x4 f32. */
 void sfm_parse_extrinsic(const double *pose7, float *extrinsic16);
+/* The interpolating pose front-end of the TSDF_Python prototype (src/TSDF_Python/main.py:127-138,
+ * tsdf_utils.py:80-100): pose at `timestamp` between two groundtruth.txt entries a8, b8 =
+ * {ts, tx, ty, tz, qx, qy, qz, qw}; pose7_out = {tx, ty, tz, qx, qy, qz, qw}, ready for sfm_parse_extrinsic.
+ * (kernel.cpp takes the next entry without interpolating, kernel.cpp:97-98.) */
+void sfm_interpolate_pose(const double *a8, const double *b8, double timestamp, double *pose7_out);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,7 @@ SYMBOLS = {
     "sfm_debug_divcheck": (_i, [_f, C.c_uint, _i, _i, _f, C.POINTER(C.c_uint64)]),
     "sfm_mean_depth": (_f, [_vp, _i]),
     "sfm_parse_extrinsic": (None, [_vp, _vp]),
+    "sfm_interpolate_pose": (None, [_vp, _vp, C.c_double, _vp]),
 }
 
 _lib = None

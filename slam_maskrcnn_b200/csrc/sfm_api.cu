@@ -1660,4 +1660,31 @@ void sfm_parse_extrinsic(const double *p, float *extrinsic16) {  // utils.cu:8-2
 	if (!mat4_inv(m, extrinsic16)) memcpy(extrinsic16, m, sizeof(m));
 }
 
+/* Pose at `timestamp` between two trajectory entries {ts, tx, ty, tz, qx, qy, qz, qw}: translation lerp
+ * (src/TSDF_Python/main.py:133-135) and quaternion slerp exactly as src/TSDF_Python/tsdf_utils.py:80-100
+ * (normalise, flip to the same hemisphere, linear blend WITHOUT renormalisation above dot 0.9995). */
+void sfm_interpolate_pose(const double *a8, const double *b8, double timestamp, double *pose7_out) {
+	const double t = (timestamp - a8[0]) / (b8[0] - a8[0]);
+	for (int k = 0; k < 3; k++) pose7_out[k] = (b8[1 + k] - a8[1 + k]) * t + a8[1 + k];
+	double q1[4], q2[4];
+	double n1 = 0, n2 = 0;
+	for (int k = 0; k < 4; k++) { n1 += a8[4 + k] * a8[4 + k]; n2 += b8[4 + k] * b8[4 + k]; }
+	n1 = sqrt(n1); n2 = sqrt(n2);
+	double dot = 0;
+	for (int k = 0; k < 4; k++) { q1[k] = a8[4 + k] / n1; q2[k] = b8[4 + k] / n2; }
+	for (int k = 0; k < 4; k++) dot += q1[k] * q2[k];
+	if (dot < 0) {
+		for (int k = 0; k < 4; k++) q1[k] = -q1[k];
+		dot = -dot;
+	}
+	if (dot > 0.9995) {
+		for (int k = 0; k < 4; k++) pose7_out[3 + k] = q1[k] + t * (q2[k] - q1[k]);
+		return;
+	}
+	dot = std::max(std::min(dot, 1.0), -1.0);
+	const double theta0 = acos(dot), theta = theta0 * t;
+	const double s1 = cos(theta) - dot * sin(theta) / sin(theta0), s2 = sin(theta) / sin(theta0);
+	for (int k = 0; k < 4; k++) pose7_out[3 + k] = s1 * q1[k] + s2 * q2[k];
+}
+
 }  // extern "C"

@@ -367,6 +367,17 @@ def mean_depth(depth):
     return float(_lib.load().sfm_mean_depth(_ptr(d), d.size))
 
 
+def interpolate_pose(a8, b8, timestamp):
+    """Pose {tx,ty,tz,qx,qy,qz,qw} at `timestamp` between two trajectory entries {ts, tx..qw}: lerp + slerp
+    as the TSDF_Python prototype does (main.py:127-138, tsdf_utils.py:80-100)."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(a8, np.float64).reshape(8)
+    b = np.ascontiguousarray(b8, np.float64).reshape(8)
+    out = np.empty(7, np.float64)
+    lib.sfm_interpolate_pose(_ptr(a), _ptr(b), C.c_double(float(timestamp)), _ptr(out))
+    return out
+
+
 def parse_extrinsic(pose7):
     """utils.cu:8-24: {tx,ty,tz,qx,qy,qz,qw} -> world->camera 4x4 float32."""
     p = np.ascontiguousarray(pose7, np.float64)

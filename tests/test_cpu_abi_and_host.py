@@ -150,3 +150,23 @@ def test_synthetic_sequence_shape_and_statistics():
     assert ((salt["depth"] == 0).reshape(60, 8, 80, 8).sum((1, 3)) == 0).mean() < 0.01
     flipped = (a["mask"] != 0) & (a["gt"] != 0)
     assert a["mask"].max() <= 15 and flipped.any()
+
+
+def test_pose_interpolation_matches_the_reference_slerp():
+    """sfm_interpolate_pose against tests/golden/pose_interp.npz: outputs of the reference's own slerp
+    (src/TSDF_Python/tsdf_utils.py:80-100, extracted and run by tests/golden/make_pose_golden.py) and the
+    translation lerp of main.py:133-135, on 200 seeded pose pairs (near-identical rotations, opposite
+    hemispheres, un-normalised quaternions, t = 0 and t = 1)."""
+    import os
+    from slam_maskrcnn_b200 import interpolate_pose, parse_extrinsic
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pose_interp.npz"))
+    worst = 0.0
+    for a, b, ts, want in zip(g["pose_a"], g["pose_b"], g["stamp"], g["pose_out"]):
+        got = interpolate_pose(a, b, ts)
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst < 1e-12, worst
+    # end points reproduce the trajectory entries (up to the sign / scale the function normalises away)
+    a, b = g["pose_a"][5], g["pose_b"][5]
+    for p, ts in ((a, a[0]), (b, b[0])):
+        q = interpolate_pose(a, b, ts)
+        assert np.allclose(parse_extrinsic(q), parse_extrinsic(p[1:]), atol=1e-5)
