@@ -170,3 +170,24 @@ def test_pose_interpolation_matches_the_reference_slerp():
     for p, ts in ((a, a[0]), (b, b[0])):
         q = interpolate_pose(a, b, ts)
         assert np.allclose(parse_extrinsic(q), parse_extrinsic(p[1:]), atol=1e-5)
+
+
+def test_write_ply_layout(tmp_path):
+    """Binary little-endian PLY: header fields, record size, RGB order (the planes hold BGR)."""
+    from slam_maskrcnn_b200 import write_ply
+    rng = np.random.default_rng(3)
+    xyz = rng.standard_normal((17, 3)).astype(np.float32)
+    bgr = rng.integers(0, 256, (17, 3)).astype(np.uint8)
+    lab = rng.integers(0, 16, 17).astype(np.uint8)
+    p = tmp_path / "pts.ply"
+    write_ply(str(p), xyz, bgr, lab)
+    raw = p.read_bytes()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    head = raw[:end].decode()
+    assert head.splitlines()[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 17"]
+    assert [l.split()[-1] for l in head.splitlines() if l.startswith("property")] == ["x", "y", "z", "red", "green", "blue", "label"]
+    rec = np.frombuffer(raw[end:], dtype=[("xyz", "<f4", 3), ("rgb", "u1", 3), ("label", "u1")])
+    assert len(rec) == 17 and (rec["xyz"] == xyz).all() and (rec["rgb"] == bgr[:, ::-1]).all() and (rec["label"] == lab).all()
+    write_ply(str(p), xyz, bgr)  # without labels: 15-byte records
+    raw = p.read_bytes()
+    assert len(raw) - (raw.index(b"end_header\n") + 11) == 17 * 15

@@ -194,3 +194,50 @@ def test_gloo_world2_integer_table_allreduce():
         assert p.exitcode == 0
     for r in res:
         assert all(r[1:]), f"rank {r[0]}: (int64 sum, int32 sum, first-pixel) = {r[1:]}"
+
+
+def test_work_profile_z_cost_model_on_a_fake_volume():
+    """work_profile_z with a stand-in volume (no GPU): the per-plane cost follows U and S at full z resolution,
+    scaled from the coarse x/y grid to the fine one."""
+    from slam_maskrcnn_b200 import slabs
+
+    class FakeVolume:
+        def __init__(self, dims):
+            self.dims = dims
+            self.n = 0
+
+        def integrate_raw(self, depth, color, mask, extrinsic):
+            assert not mask.any()  # the profile pass must use an all-zero label image (bin 0 counts S)
+            self.n += 1
+
+        def download(self, name):
+            cx, cy, dz = self.dims
+            if name == "weight":   # every frame touches planes [0, 60) completely
+                w = np.zeros((cx, cy, dz), np.int32)
+                w[:, :, :60] = self.n
+                return w
+            h = np.zeros((cx, cy, dz, 1), np.uint32)  # ... and updates the histogram in planes [50, 60)
+            h[:, :, 50:60, 0] = self.n
+            return h
+
+        def close(self):
+            pass
+
+    frames = [{"depth": np.zeros((4, 4), np.uint16), "color": np.zeros((4, 4, 3), np.uint8), "gt": np.zeros((4, 4), np.uint8),
+               "extrinsic": np.eye(4, dtype=np.float32)} for _ in range(3)]
+    made = []
+
+    def factory(pdims):
+        made.append(pdims)
+        return FakeVolume(pdims)
+
+    prof, u, s = slabs.work_profile_z(factory, frames, (256, 512, 96), coarse_xy=64)
+    assert made == [(64, 64, 96)]
+    assert abs(prof.sum() - 1.0) < 1e-12 and len(prof) == 96
+    assert np.allclose(u[:60], 256 * 512) and np.allclose(u[60:], 0)          # per frame, at the fine x/y resolution
+    assert np.allclose(s[50:60], 256 * 512) and np.allclose(s[:50], 0)
+    free, surf, empty = prof[10], prof[55], prof[80]
+    assert surf / free == pytest.approx((slabs.COST_SURFACE + slabs.COST_VISIT) / (slabs.COST_FREE + slabs.COST_VISIT))
+    assert empty / free == pytest.approx(slabs.COST_VISIT / (slabs.COST_FREE + slabs.COST_VISIT))
+    plan = slabs.plan_slabs(96, 4, prof)
+    assert sum(n for _, n in plan) == 96 and any(z0 >= 48 and n == 8 for z0, n in plan), plan
