@@ -54,3 +54,50 @@ def test_cpp_driver_fuses_and_renders(tmp_path):
     data = open(ppm, "rb").read()
     body = np.frombuffer(data[data.index(b"255\n") + 4:], np.uint8).reshape(480, 640, 3)
     assert (body[..., ::-1] == img).all(), "C++ driver and Python mirror must render the same image"
+
+
+def test_cpp_driver_colour_view_ply_and_interpolated_poses(tmp_path):
+    """--render-color (interp_tsdf_color view) and --ply (surface export) against the Python mirror on the same
+    sequence; --interp (lerp + slerp poses) must run and, with depth timestamps that sit on trajectory entries,
+    leave the result essentially unchanged."""
+    import cv2
+    from slam_maskrcnn_b200 import TSDF, mean_depth, parse_extrinsic
+    drv = os.path.join(ROOT, "driver", "sfm_driver")
+    if not os.path.exists(drv):
+        pytest.skip("driver/sfm_driver not built")
+    seq = str(tmp_path / "seq")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_sequence.py"), seq, "6", "3"], check=True)
+    ppm, cppm, ply = str(tmp_path / "l.ppm"), str(tmp_path / "c.ppm"), str(tmp_path / "s.ply")
+    base = [drv, seq, "--dim", "96", "--bins", "16", "--views", "2", "--render", ppm, "--render-color", cppm, "--ply", ply]
+    r = subprocess.run(base, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    n_pts = int(re.search(r"surface: (\d+) points", r.stdout).group(1))
+    assert n_pts > 500
+    # same fusion through the Python mirror, then the same surface
+    t = TSDF((520.9, 521.0, 325.1, 249.7), dims=(96, 96, 96), bins=16)
+    poses = {}
+    for line in open(os.path.join(seq, "groundtruth.txt")):
+        if not line.startswith("#"):
+            v = [float(x) for x in line.split()]
+            poses[f"{v[0]:.6f}"] = v[1:]
+    for n in sorted(os.listdir(os.path.join(seq, "depth"))):
+        depth = cv2.imread(os.path.join(seq, "depth", n), cv2.IMREAD_UNCHANGED)
+        rgb = cv2.imread(os.path.join(seq, "rgb", n))
+        mask = cv2.imread(os.path.join(seq, "mask", n + ".png"), cv2.IMREAD_GRAYSCALE)
+        t.parse_frame(depth, rgb, np.ascontiguousarray(mask), parse_extrinsic(poses[n[:-4]]), mean_depth(depth))
+    xyz, bgr, lab = t.vol.extract_surface()
+    assert len(xyz) == n_pts
+    raw = open(ply, "rb").read()
+    end = raw.index(b"end_header\n") + 11
+    rec = np.frombuffer(raw[end:], dtype=[("xyz", "<f4", 3), ("rgb", "u1", 3), ("label", "u1")])
+    assert len(rec) == n_pts
+    order = np.lexsort((rec["xyz"][:, 2], rec["xyz"][:, 1], rec["xyz"][:, 0]))
+    assert (rec["xyz"][order] == xyz).all()
+    data = open(cppm, "rb").read()
+    body = np.frombuffer(data[data.index(b"255\n") + 4:], np.uint8).reshape(480, 640, 3)
+    assert body.any(), "the colour view is empty"
+    # interpolated poses
+    r2 = subprocess.run(base + ["--interp"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout
+    n2 = int(re.search(r"surface: (\d+) points", r2.stdout).group(1))
+    assert abs(n2 - n_pts) <= 0.05 * n_pts
