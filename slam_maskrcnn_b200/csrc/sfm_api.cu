@@ -322,7 +322,10 @@ void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, lo
 
 template <bool VEC4>
 void launch_classify(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
-	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL), tma = !(v->desc.flags & SFM_FLAG_NO_TMA);
+	// the TMA-staged tile grids must fit a block's shared memory next to its brick lists (frames up to about
+	// 1600 x 1200); larger frames read the grids through L1 like SFM_FLAG_NO_TMA does
+	const bool fits = v->tile_bytes + 2 * (size_t)kSbPerBlock * 32 * sizeof(uint32_t) <= 160 * 1024;
+	const bool cull = !(v->desc.flags & SFM_FLAG_NO_CULL), tma = !(v->desc.flags & SFM_FLAG_NO_TMA) && fits;
 	if (!cull) launch_classify2<VEC4, false, false>(v, f, wl, nsb);
 	else if (tma) launch_classify2<VEC4, true, true>(v, f, wl, nsb);
 	else launch_classify2<VEC4, true, false>(v, f, wl, nsb);
