@@ -241,3 +241,97 @@ def test_work_profile_z_cost_model_on_a_fake_volume():
     assert empty / free == pytest.approx(slabs.COST_VISIT / (slabs.COST_FREE + slabs.COST_VISIT))
     plan = slabs.plan_slabs(96, 4, prof)
     assert sum(n for _, n in plan) == 96 and any(z0 >= 48 and n == 8 for z0, n in plan), plan
+
+
+def _fuse_worker(rank, world, port, q):
+    """SlabVolume.fuse_packed_sharded over gloo with a stand-in Volume (no GPU): the host side must issue the
+    three MIN all-reduces between the march stages, let exactly rank 0 take the pixel counts, SUM the integer
+    tables (int64 part and int32 part separately) and hand every rank the SAME reduced tables."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from slam_maskrcnn_b200 import slabs
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H, L = 8, 4, 4
+        n = W * H
+        n64, ntot = (2 * L * L + L) * 8, (2 * L * L + L) * 8 + (L * L + 4 * L) * 4
+
+        def view(ptr, count, dtype):
+            size = np.dtype(dtype).itemsize
+            return np.frombuffer((ctypes.c_char * (count * size)).from_address(ptr), dtype=dtype)
+
+        class Info:
+            n_obs = 3
+
+        class FakeVol:
+            bins = L
+            log = []
+
+            def info(self):
+                return Info()
+
+            def shard_backproj_stage(self, stage, E, ev1, ev2, out):
+                o = view(out, n, np.int64)
+                if stage > 1:   # the previous stages arrive REDUCED: min over ranks of (1000*stage' + 10*rank + pixel)
+                    assert (view(ev1, n, np.int64) == 1000 + np.arange(n)).all()
+                if stage > 2:
+                    assert (view(ev2, n, np.int64) == 2000 + np.arange(n)).all()
+                o[:] = 1000 * stage + 10 * rank + np.arange(n)
+                self.log.append(("stage", stage))
+
+            def fold_table_bytes(self):
+                return n64, ntot
+
+            def shard_fold(self, d_mask, d_keys, do_counts, d_tables):
+                assert (view(d_keys, n, np.int64) == 3000 + np.arange(n)).all()   # the composited keys
+                assert bool(do_counts) == (rank == 0)
+                t = view(d_tables, ntot, np.uint8)
+                t[:n64].view(np.int64)[:] = (rank + 1) * 2 ** 40 + np.arange(n64 // 8)
+                t[n64:].view(np.int32)[:] = (rank + 1) * 7
+                self.log.append(("fold", bool(do_counts)))
+
+            def shard_merge_finish(self, d_tables, d_mask):
+                t = view(d_tables, ntot, np.uint8)
+                tri = world * (world + 1) // 2
+                ok64 = (t[:n64].view(np.int64) == tri * 2 ** 40 + world * np.arange(n64 // 8)).all()
+                ok32 = (t[n64:].view(np.int32) == tri * 7).all()
+                self.log.append(("finish", bool(ok64), bool(ok32)))
+                m = view(d_mask, n, np.uint8)
+                m[:] = 9   # "relabel"
+                return np.arange(256, dtype=np.uint8), "report"
+
+            def shard_first_frame(self, d_mask):
+                self.log.append(("first",))
+
+            def integrate_dev(self, d_depth, d_color, d_mask, E):
+                self.log.append(("integrate", int(view(d_mask, n, np.uint8)[0])))
+
+        sv = slabs.SlabVolume.__new__(slabs.SlabVolume)
+        sv.rank, sv.world, sv.vol, sv.width, sv.height = rank, world, FakeVol(), W, H
+        packed = torch.zeros(slabs.frame_nbytes(W, H), dtype=torch.uint8)
+        lut, rep = sv.fuse_packed_sharded(packed, np.eye(4, dtype=np.float32))
+        log = sv.vol.log
+        ok = (log == [("stage", 1), ("stage", 2), ("stage", 3), ("fold", rank == 0), ("finish", True, True), ("integrate", 9)]
+              and rep == "report" and (lut == np.arange(256)).all())
+        q.put((rank, bool(ok), log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_fuse_host_logic():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_fuse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1], f"rank {r[0]}: {r[2]}"
