@@ -287,7 +287,11 @@ def run_ours(args):
     else:
         plan = slabs_mod.plan_slabs(dims[2], world)
     def make_volume(plan):
-        v = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=plan[rank], flags=args.flags)
+        # FLAG_ASYNC_SOURCES: every frame of the pool has its own pinned buffer that is never rewritten, so the
+        # host-buffer call may return before its H2D copy has finished (sfm_b200.h, "Buffer lifetime")
+        from slam_maskrcnn_b200 import FLAG_ASYNC_SOURCES
+        v = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=plan[rank],
+                   flags=args.flags | FLAG_ASYNC_SOURCES)
         v.set_stream(torch.cuda.current_stream().cuda_stream)
         v.set_bounds(*place)
         v.synchronize()

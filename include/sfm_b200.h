@@ -51,8 +51,17 @@ enum {
 	SFM_FLAG_NO_TMA = 2,       /* read the per-frame depth tile grids through L1 instead of staging them into
 	                              shared memory with a TMA bulk copy (cp.async.bulk)                      */
 	SFM_FLAG_SYNC_EVERY_CALL = 4, /* cudaStreamSynchronize before returning from every call        */
-	SFM_FLAG_GENERIC_K = 8     /* evaluate K*c with all nine terms even when K has the pinhole zero pattern
+	SFM_FLAG_GENERIC_K = 8,    /* evaluate K*c with all nine terms even when K has the pinhole zero pattern
 	                              (the default drops the exact-zero terms; same results)                  */
+	SFM_FLAG_NO_QUADS = 16,    /* send every quad (4 z voxels of a column) of a listed brick through the exact
+	                              per-voxel path instead of classifying quads first (same results)        */
+	SFM_FLAG_DEBUG_ABLATE = 32, /* profiling builds only: honour the SFM_DEBUG_ABLATE environment variable
+	                              (switches parts of the integrate kernel OFF; results are then wrong)    */
+	SFM_FLAG_ASYNC_SOURCES = 64 /* pinned-host / device frame buffers passed to sfm_integrate_raw,
+	                              sfm_fuse_frame and sfm_parse_frame may still be read by the GPU after the call
+	                              returns: the caller keeps them unchanged until sfm_wait_uploads() or
+	                              sfm_synchronize().  Without it every call returns only after its frame has
+	                              been copied, like the reference's blocking cudaMemcpy (tsdf.cu:422-424)   */
 };
 
 /* Creation parameters.  Defaults (sfm_desc_default) are the reference's hard-coded values. */
@@ -129,7 +138,13 @@ int sfm_parse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, 
 int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
 	const float *extrinsic2init16);
 
-/* tsdf_kernel only (tsdf.cu:18-70, launch tsdf.cu:472-488): parity hook, host frame buffers. */
+/* tsdf_kernel only (tsdf.cu:18-70, launch tsdf.cu:472-488): parity hook, host frame buffers.
+ * Buffer lifetime (this call, sfm_fuse_frame, sfm_parse_frame, sfm_overlap_tables): the frame buffers are the
+ * caller's and may be reused as soon as the call returns, as with the reference's blocking cudaMemcpy
+ * (tsdf.cu:422-424, 470) -- pageable memory is staged into a pinned bounce buffer, pinned-host / device memory
+ * is copied by the copy engine and the call waits for that copy.  A caller that sets SFM_FLAG_ASYNC_SOURCES
+ * gets the call back before the copy has finished and must leave pinned / device buffers unchanged until
+ * sfm_wait_uploads() (or sfm_synchronize()) returns. */
 int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color, const uint8_t *mask,
 	const float *extrinsic2init16);
 /* Same with frame buffers already resident in device memory (multi-GPU: after the NCCL broadcast). */
@@ -164,8 +179,13 @@ int sfm_last_merge(sfm_volume *v, sfm_merge_report *report);
 int sfm_download(sfm_volume *v, int plane, void *dst, size_t bytes);
 int sfm_upload(sfm_volume *v, int plane, const void *src, size_t bytes);
 size_t sfm_plane_bytes(sfm_volume *v, int plane);
-/* The reference exposes its device pointers as public members (tsdf.cuh:24-43). */
+/* The reference exposes its device pointers as public members (tsdf.cuh:24-43).  A caller that WRITES the SDF
+ * plane through this pointer must call sfm_planes_written() afterwards: the ray-marcher keeps a map of the
+ * blocks that ever held a near-surface value and skips the others (sfm_upload does this itself). */
 void *sfm_plane_device_ptr(sfm_volume *v, int plane);
+int sfm_planes_written(sfm_volume *v);
+/* Blocks until every frame copy issued so far has read its source buffers (see SFM_FLAG_ASYNC_SOURCES). */
+int sfm_wait_uploads(sfm_volume *v);
 
 /* show_tsdf_kernel (viewer.cu:17-86, launch 152-166).  bgr u8[h*w*3] host; t_opt f32[h*w],
  * label_opt u8[h*w] optional. */

@@ -50,6 +50,9 @@ FLAG_NO_CULL = 1
 FLAG_NO_TMA = 2
 FLAG_GENERIC_K = 8
 FLAG_SYNC_EVERY_CALL = 4
+FLAG_NO_QUADS = 16
+FLAG_DEBUG_ABLATE = 32
+FLAG_ASYNC_SOURCES = 64
 PLANE_SDF, PLANE_WEIGHT, PLANE_COLOR, PLANE_HIST = 0, 1, 2, 3
 
 # every symbol include/sfm_b200.h declares: name -> (restype, argtypes)
@@ -85,6 +88,8 @@ SYMBOLS = {
     "sfm_palette": (None, [_vp, _i]),
     "sfm_get_info": (_i, [_vp, C.POINTER(Info)]),
     "sfm_synchronize": (_i, [_vp]),
+    "sfm_wait_uploads": (_i, [_vp]),
+    "sfm_planes_written": (_i, [_vp]),
     "sfm_set_stream": (_i, [_vp, _vp]),
     "sfm_timer_start": (_i, [_vp]),
     "sfm_timer_stop": (_i, [_vp, C.POINTER(_f)]),

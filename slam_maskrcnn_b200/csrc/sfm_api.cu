@@ -110,13 +110,15 @@ struct sfm_volume {
 	unsigned long long *h_stat_ring = nullptr;   // pinned, kStatRing x 2*kStatSlots
 	cudaEvent_t ev_stat[kStatRing] = {};
 	uint64_t stat_tickets = 0;
-	// Per-frame preparation contexts, double buffered: what K0 + K1a produce for K1b.  K0 / K1a of frame i+1
+	// Per-frame preparation contexts (kCtx = 3 of them, rotating): what K0 + K1a produce for K1b.  K0 / K1a of frame i+1
 	// run on prep_stream while K1b of frame i still reads the other context on the main stream.
 	struct PrepCtx {
 		uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
 		float *d_depth_m = nullptr;
+		float2 *d_win = nullptr;                     // windowed depth range per pixel (K0b -> K1b quad classification)
 		unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
-		uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
+		uint32_t *d_list_mixed = nullptr;                          // K1a pass 2 -> pass 3: MIXED brick ids (one slot per brick)
+		uint2 *d_list_bricks = nullptr, *d_list_exact = nullptr;   // K1a -> K1b: brick entries (one slot per brick), EXACT quads (one per quad)
 		cudaEvent_t ev_ready = nullptr;  // K1a of the frame that uses this context is done (prep_stream)
 		cudaEvent_t ev_free = nullptr;   // K1b of that frame is done (main stream): the context may be rewritten
 	} ctx[3];
@@ -171,6 +173,11 @@ struct sfm_volume {
 	uint64_t n_integrate = 0;
 	uint64_t launches = 0;
 	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
+	// per-handle (= per-device) launch state: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
+	size_t k1a_smem_set = 0;   // dynamic shared memory K1a has been configured for on this handle's device
+	int k1b_per_sm[8] = {};    // resident K1b blocks per SM, per kernel instantiation (0 = not queried yet)
+	int k1q_blocks_per_sm = 8; // grid of quad_kernel (K1a pass 3), blocks per SM
+	int debug_ablate = 0;      // SFM_DEBUG_ABLATE, read once at creation and only under SFM_FLAG_DEBUG_ABLATE
 };
 
 namespace {
@@ -255,6 +262,10 @@ int upload_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, con
 	CU(cudaEventRecord(v->ev_uploaded[b], v->copy_stream));
 	CU(cudaStreamWaitEvent(v->stream, v->ev_uploaded[b], 0));
 	v->frame_open = true;
+	// Lifetime of the caller's buffers (sfm_b200.h): pageable sources were copied into the bounce buffer above;
+	// pinned / device sources are read by the copy engine, so the call waits for the copy unless the caller
+	// took that responsibility with SFM_FLAG_ASYNC_SOURCES
+	if (direct && !(v->desc.flags & SFM_FLAG_ASYNC_SOURCES)) CU(cudaEventSynchronize(v->ev_uploaded[b]));
 	return SFM_OK;
 }
 
@@ -278,6 +289,7 @@ FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, con
 	f.tilemin = c.d_tilemin;
 	f.tile_bytes = (unsigned)v->tile_bytes;
 	f.depth_m = c.d_depth_m;
+	f.win = c.d_win;
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
 	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
@@ -295,20 +307,32 @@ FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, con
 	f.cull_t = tt;
 	f.cull_k2 = k2;
 	f.cull_slack0 = 1.f + 1e-3f * std::max(k0, k1) / std::max(k2, 1e-20f);
-	f.debug = getenv("SFM_DEBUG_ABLATE") ? atoi(getenv("SFM_DEBUG_ABLATE")) : 0;
+	f.cull_scale = lin * (std::max(fabsf(v->g.sx), fabsf(v->g.ex)) + std::max(fabsf(v->g.sy), fabsf(v->g.ey)) +
+		std::max(fabsf(v->g.sz), fabsf(v->g.ez)) + 1.f) + tt;
+	f.cull_kx = k0;
+	f.cull_ky = k1;
+	f.debug = v->debug_ablate | ((v->desc.flags & SFM_FLAG_NO_QUADS) ? 64 : 0);
 	return f;
 }
 
-// K1a: brick classification into the work lists
+// pinhole pattern of K (see cam_to_screen): the only one the reference can build (tsdf.cu:137-150).  The generic
+// path stays for arbitrary K and behind SFM_FLAG_GENERIC_K (A/B parity test).
+bool canonical_k(const sfm_volume *v, const FrameView &f) {
+	const float *K = f.K;
+	bool canon = !(v->desc.flags & SFM_FLAG_GENERIC_K) && K[1] == 0.f && K[3] == 0.f && K[6] == 0.f && K[7] == 0.f && K[8] == 1.f;
+	for (int i = 0; i < 12 && canon; i++) canon = std::isfinite(f.E[i]) && fabsf(f.E[i]) < 1e15f;
+	return canon;
+}
+
+// K1a: classification into the work lists (classify_kernel: boxes and bricks; quad_kernel: the quads of MIXED bricks)
 template <bool VEC4, bool CULL, bool TMA_TILES>
 void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
 	// dynamic shared memory: [TMA-staged tile grids] [block-local MIXED list] [block-local FREE list]
 	const size_t smem = (TMA_TILES ? v->tile_bytes : 0) + 2 * (size_t)kSbPerBlock * 32 * sizeof(uint32_t);
 	auto kern = classify_kernel<VEC4, CULL, TMA_TILES>;
-	static size_t smem_set = 0;
-	if (smem > 48 * 1024 && smem_set != smem) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		smem_set = smem;
+	if (smem > 48 * 1024 && v->k1a_smem_set != smem) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;  // the launch check reports it
+		v->k1a_smem_set = smem;
 	}
 	// persistent-ish grid: 1024 threads per SM, more blocks when one would otherwise see > kSbPerBlock super-blocks
 	constexpr int warps = kK1aThreads / 32;
@@ -331,38 +355,51 @@ void launch_classify(sfm_volume *v, const FrameView &f, const WorkLists &wl, lon
 	else launch_classify2<VEC4, true, false>(v, f, wl, nsb);
 }
 
+// pass 3: quads of the MIXED bricks.  The list length is only known on the device: a grid of resident warps walks it.
+template <bool VEC4>
+void launch_quads(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
+	// quad classification (classify_quad) assumes the pinhole K and the 128-bit path
+	const bool quads = VEC4 && canonical_k(v, f) && !(v->desc.flags & SFM_FLAG_NO_QUADS);
+	const size_t smem = (size_t)(kK1aThreads / 32) * (kStageB + kStageX) * sizeof(uint2);
+	const int blocks = v->num_sms * v->k1q_blocks_per_sm;
+	if (quads) quad_kernel<VEC4, VEC4><<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
+	else quad_kernel<VEC4, false><<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
+}
+
 // K1b: update of the listed bricks
 template <int VEC, bool LABELS, bool KCANON>
-void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
+void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl, const int32_t *gate) {
 	// persistent grid: one resident wave (occupancy x SM count); the warps pull bricks from the lists.
 	// dynamic shared memory: the per-warp surface queues
 	constexpr int warps = kK1Threads / 32;
 	const size_t smem = warps * kQueue * sizeof(uint4);
-	static int per_sm = 0;
+	int &per_sm = v->k1b_per_sm[(VEC == 4 ? 4 : 0) + (LABELS ? 2 : 0) + (KCANON ? 1 : 0)];
 	auto kern = integrate_kernel<VEC, LABELS, KCANON>;
 	if (!per_sm) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;  // the launch check reports it
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kK1Threads, smem) != cudaSuccess || per_sm < 1)
 			per_sm = 1;
-		// one block slot per SM is left to K1a of the next frame, which runs concurrently on prep_stream
-		if (per_sm * kK1Threads >= 1024) per_sm = (1024 - kK1aThreads) / kK1Threads;
+		// one block slot per SM is left to K1a of the next frame, which runs concurrently on prep_stream: threads
+		// and registers of the resident K1b blocks plus one K1a block must fit the SM (registers are allocated per
+		// warp in units of 256)
+		cudaFuncAttributes ab{}, aa{};
+		if (cudaFuncGetAttributes(&ab, kern) == cudaSuccess &&
+			cudaFuncGetAttributes(&aa, classify_kernel<true, true, true>) == cudaSuccess) {
+			const int rb = ((ab.numRegs + 7) / 8) * 8 * kK1Threads, ra = ((aa.numRegs + 7) / 8) * 8 * kK1aThreads;
+			while (per_sm > 1 && (per_sm * kK1Threads + kK1aThreads > 1024 || per_sm * rb + ra > 65536)) per_sm--;
+		} else if (per_sm * kK1Threads >= 1024) per_sm = (1024 - kK1aThreads) / kK1Threads;
 		if (const char *e = getenv("SFM_K1B_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
 	}
 	const long long want = ((long long)v->nbricks + warps - 1) / warps;
-	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));
-	kern<<<blocks, kK1Threads, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err);
+	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));  // persistent: one resident wave
+	kern<<<blocks, kK1Threads, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err, gate);
 }
 
 template <int VEC, bool LABELS>
-void launch_update(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
-	// pinhole pattern of K (see cam_to_screen): the only one the reference can build (tsdf.cu:137-150).
-	// The generic path stays for arbitrary K, for VEC = 1 and behind SFM_FLAG_GENERIC_K (A/B parity test).
-	const float *K = f.K;
-	bool canon = VEC == 4 && !(v->desc.flags & SFM_FLAG_GENERIC_K) && K[1] == 0.f && K[3] == 0.f && K[6] == 0.f &&
-		K[7] == 0.f && K[8] == 1.f;
-	for (int i = 0; i < 12 && canon; i++) canon = std::isfinite(f.E[i]) && fabsf(f.E[i]) < 1e15f;
-	if (VEC == 4 && canon) launch_update2<VEC, LABELS, VEC == 4>(v, f, wl);
-	else launch_update2<VEC, LABELS, false>(v, f, wl);
+void launch_update(sfm_volume *v, const FrameView &f, const WorkLists &wl, const int32_t *gate) {
+	const bool canon = VEC == 4 && canonical_k(v, f);
+	if (VEC == 4 && canon) launch_update2<VEC, LABELS, VEC == 4>(v, f, wl, gate);
+	else launch_update2<VEC, LABELS, false>(v, f, wl, gate);
 }
 
 // K0 + K1a + K1b on device-resident frame images.
@@ -396,16 +433,22 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 	prep_frame_kernel<<<prep_blocks, 256, 0, v->prep_stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
 		v->bins, v->desc.depth_scale, c.d_tilemax, c.d_tilemin, c.d_depth_m, v->d_err, c.d_work);
 	LAUNCH_CHECK(v);
+	window_kernel<<<dim3((v->W + kWinTX - 1) / kWinTX, (v->H + kWinTY - 1) / kWinTY), 256, 0, v->prep_stream>>>(f.depth, v->W, v->H,
+		v->desc.depth_scale, c.d_win);
+	LAUNCH_CHECK(v);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one z chunk (k_integrate.cuh)
 	const int cpw = vec4 ? (32 >> v->g.zl_log2) : 1, chunk = vec4 ? (4 << v->g.zl_log2) : 32;
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
 	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
 	if (nsb >= (1LL << 31)) return fail(SFM_ERR_INVALID, "volume too large for the 31-bit super-block ids");
-	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
+	const WorkLists wl{c.d_list_mixed, c.d_list_bricks, c.d_list_exact, c.d_work};
 	CU(cudaEventRecord(v->ev_k0[slot], v->prep_stream));
 	if (vec4) launch_classify<true>(v, f, wl, nsb);
 	else launch_classify<false>(v, f, wl, nsb);
+	LAUNCH_CHECK(v);
+	if (vec4) launch_quads<true>(v, f, wl);
+	else launch_quads<false>(v, f, wl);
 	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_km[slot], v->prep_stream));
 	CU(cudaEventRecord(c.ev_ready, v->prep_stream));
@@ -413,20 +456,20 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 }
 
 // second half: K1b on the main stream, after the context enqueue_prepare filled
-int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16) {
+int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const void *d_mask, const float *E16, const int32_t *gate = nullptr) {
 	sfm_volume::PrepCtx &c = v->ctx[v->n_integrate % sfm_volume::kCtx];
 	const FrameView f = make_frame_view(v, c, d_depth, d_rgb, d_mask, E16);
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	const bool vec4 = (v->g.nz % 4 == 0);
-	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
+	const WorkLists wl{c.d_list_mixed, c.d_list_bricks, c.d_list_exact, c.d_work};
 	CU(cudaStreamWaitEvent(v->stream, c.ev_ready, 0));
 	CU(cudaEventRecord(v->ev_kb[slot], v->stream));
 	if (vec4) {
-		if (v->bins > 0) launch_update<4, true>(v, f, wl);
-		else launch_update<4, false>(v, f, wl);
+		if (v->bins > 0) launch_update<4, true>(v, f, wl, gate);
+		else launch_update<4, false>(v, f, wl, gate);
 	} else {
-		if (v->bins > 0) launch_update<1, true>(v, f, wl);
-		else launch_update<1, false>(v, f, wl);
+		if (v->bins > 0) launch_update<1, true>(v, f, wl, gate);
+		else launch_update<1, false>(v, f, wl, gate);
 	}
 	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_k1[slot], v->stream));
@@ -539,7 +582,7 @@ FoldLayout fold_layout(int L) {
 	return f;
 }
 
-__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut);
+__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut, const int32_t *__restrict__ gate);
 void combine_tables(const sfm_volume *v, int max_obj_now, double *A, uint32_t *C);
 void decide(const sfm_volume *v, const double *A, const uint32_t *C, int max_obj_now, const unsigned *first_pix,
 	int *num_objs, sfm_merge_report *rep);
@@ -676,7 +719,9 @@ void decide(const sfm_volume *v, const double *A, const uint32_t *C, int max_obj
 	rep->margin = margin;
 }
 
-__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut) {
+// `gate` (nullable): set when the decision overflowed the bins -- the mask then keeps the caller's labels
+__global__ void relabel_kernel(uint8_t *__restrict__ mask, int n, const uint8_t *__restrict__ lut, const int32_t *__restrict__ gate) {
+	if (gate && *gate) return;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) mask[i] = lut[mask[i]];
 }
@@ -784,7 +829,7 @@ int enqueue_device_decision(sfm_volume *v, uint8_t *d_tables, uint8_t *d_mask) {
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(v->h_merge, v->d_merge, sizeof(MergeOut), cudaMemcpyDeviceToHost, v->stream));
 	CU(cudaEventRecord(v->ev_merge, v->stream));
-	relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(d_mask, (int)npx, out->lut);
+	relabel_kernel<<<(int)((npx + 255) / 256), 256, 0, v->stream>>>(d_mask, (int)npx, out->lut, &out->overflow);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
 }
@@ -857,6 +902,10 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 
 	sfm_volume *v = new sfm_volume();
 	v->desc = *desc;
+	if (desc->flags & SFM_FLAG_DEBUG_ABLATE) {  // profiling only: a stray environment variable alone changes nothing
+		if (const char *e = getenv("SFM_DEBUG_ABLATE")) v->debug_ablate = atoi(e) & ~64;
+		if (const char *e = getenv("SFM_K1Q_BLOCKS_PER_SM")) v->k1q_blocks_per_sm = std::max(1, std::min(16, atoi(e)));
+	}
 	v->bins = desc->bins;
 	v->W = desc->width;
 	v->H = desc->height;
@@ -938,8 +987,9 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		CU_OR_DESTROY(cudaMemset(c.d_tilemax, 0, v->tile_bytes));
 		c.d_tilemin = c.d_tilemax + (size_t)v->TW * v->TH;
 		CU_OR_DESTROY(cudaMalloc(&c.d_depth_m, npx * 4));
-		CU_OR_DESTROY(cudaMalloc(&c.d_work, 16));
-		CU_OR_DESTROY(cudaMemset(c.d_work, 0, 16));
+		CU_OR_DESTROY(cudaMalloc(&c.d_win, npx * sizeof(float2)));
+		CU_OR_DESTROY(cudaMalloc(&c.d_work, 32));
+		CU_OR_DESTROY(cudaMemset(c.d_work, 0, 32));
 		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
 		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_free, cudaEventDisableTiming));
 	}
@@ -971,9 +1021,13 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 			return fail(SFM_ERR_INVALID, "volume too large for the packed brick ids (x <= 2048, y <= 8192 (2048 when nz % 4 != 0), nz <= 32768)");
 		}
 		v->nbricks = (size_t)v->g.Dx * rows * chunks;
+		// exact-quad list: one slot per quad of the volume (worst case: every quad of every brick is EXACT, which is
+		// what SFM_FLAG_NO_CULL + SFM_FLAG_NO_QUADS produce); 2 bytes per voxel on the 128-bit path
+		const size_t nquads = vec4 ? v->nvox / 4 : v->nbricks * 32;
 		for (auto &c : v->ctx) {
-			CU_OR_DESTROY(cudaMalloc(&c.d_list_mixed, v->nbricks * 4));
-			CU_OR_DESTROY(cudaMalloc(&c.d_list_free, v->nbricks * 4));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_mixed, v->nbricks * sizeof(uint32_t)));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_bricks, v->nbricks * sizeof(uint2)));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_exact, nquads * sizeof(uint2)));
 		}
 	}
 	v->num_sms = prop.multiProcessorCount;
@@ -1022,7 +1076,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
 	if (v->prep_stream) cudaStreamDestroy(v->prep_stream);
 	for (auto &c : v->ctx) {
-		cudaFree(c.d_tilemax); cudaFree(c.d_depth_m); cudaFree(c.d_work); cudaFree(c.d_list_mixed); cudaFree(c.d_list_free);
+		cudaFree(c.d_tilemax); cudaFree(c.d_depth_m); cudaFree(c.d_win); cudaFree(c.d_work); cudaFree(c.d_list_mixed); cudaFree(c.d_list_bricks); cudaFree(c.d_list_exact);
 		if (c.ev_ready) cudaEventDestroy(c.ev_ready);
 		if (c.ev_free) cudaEventDestroy(c.ev_free);
 	}
@@ -1131,8 +1185,10 @@ int sfm_integrate_raw(sfm_volume *v, const uint16_t *depth, const uint8_t *color
 	int rc = upload_frame(v, depth, color, v->bins > 0 ? mask : nullptr);
 	if (rc) return rc;
 	rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
-	if (rc) return rc;
-	return release_frame(v);
+	const std::string keep = g_err;
+	const int rc2 = release_frame(v);
+	if (rc) { g_err = keep; return rc; }
+	return rc2;
 }
 
 int sfm_overlap_tables(sfm_volume *v, const float *E16, const uint8_t *mask, double *A, uint32_t *C) {
@@ -1148,9 +1204,12 @@ int sfm_overlap_tables(sfm_volume *v, const float *E16, const uint8_t *mask, dou
 	rc = upload_frame(v, nullptr, nullptr, mask);
 	if (rc) return rc;
 	rc = run_fold(v, E16, v->d_mask);
-	if (rc) return rc;
-	rc = release_frame(v);
-	if (rc) return rc;
+	{
+		const std::string keep = g_err;
+		const int rc2 = release_frame(v);
+		if (rc) { g_err = keep; return rc; }
+		if (rc2) return rc2;
+	}
 	combine_tables(v, mx + 1, A, C);
 	return SFM_OK;
 }
@@ -1176,51 +1235,63 @@ int sfm_last_merge(sfm_volume *v, sfm_merge_report *report) {
 	return SFM_OK;
 }
 
+namespace {
+// body of sfm_fuse_frame after the upload; the caller releases the frame buffer whatever this returns
+int fuse_uploaded_frame(sfm_volume *v, uint8_t *mask_inout, int mx, const float *E16) {
+	const size_t npx = (size_t)v->W * v->H;
+	const cudaEvent_t up = v->ev_uploaded[v->frame_cur];
+	if (v->bins <= 0 || v->n_obs == 0) {
+		if (v->bins > 0) v->num_objs = mx + 1;  // tsdf.cu:464-467
+		return integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, up);
+	}
+	// tsdf.cu:426-461: back-project, fold, decide, relabel
+	int rc = require_full_volume(v, "sfm_fuse_frame (merge)");
+	if (rc) return rc;
+	// everything up to the integration is enqueued without a host round trip: march, fold, decision
+	// and relabel on the device; the host only waits for the 2 KB report to relabel ITS copy of the
+	// mask, which overlaps the integrate kernels
+	// (K0 + K1a of this frame run on prep_stream meanwhile: they only need the uploaded images; the
+	// relabel waits for them because K0 range-checks the incoming labels)
+	rc = enqueue_prepare(v, v->d_depth, v->d_rgb, v->d_mask, E16, up);
+	if (rc) return rc;
+	rc = enqueue_march_fold(v, E16, v->d_mask);
+	if (rc) return rc;
+	CU(cudaStreamWaitEvent(v->stream, v->ctx[v->n_integrate % sfm_volume::kCtx].ev_ready, 0));
+	rc = enqueue_device_decision(v, v->d_fold, v->d_mask);
+	if (rc) return rc;
+	// the decision may overflow the bins (a fresh id >= bins: the reference corrupts its histogram there,
+	// tsdf.cu:61,383).  Relabel and update are gated on the device by that flag, so a failing frame leaves
+	// the volume, n_obs and num_objs exactly as they were and the caller may retry or skip it.
+	const uint32_t n_obs_before = v->n_obs;
+	rc = enqueue_update(v, v->d_depth, v->d_rgb, v->d_mask, E16, &((const MergeOut *)v->d_merge)->overflow);
+	if (rc) return rc;
+	uint8_t lut[256];
+	rc = finish_device_decision(v, lut);
+	if (rc) {
+		v->n_obs = n_obs_before;
+		return rc;
+	}
+	for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // tsdf.cu:372-389 does it in place
+	return SFM_OK;
+}
+}  // namespace
+
 int sfm_fuse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout, const float *E16) {
 	if (!v || !depth || !color || !E16 || (v->bins > 0 && !mask_inout)) return fail(SFM_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(v->desc.device));
 	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
-	const size_t npx = (size_t)v->W * v->H;
-	int rc;
+	int mx = 0;
 	if (v->bins > 0) {
-		const int mx = max_label_host(mask_inout, npx);
+		mx = max_label_host(mask_inout, (size_t)v->W * v->H);
 		if (mx >= v->bins) return fail(SFM_ERR_INVALID, "mask carries a label >= bins");
-		rc = upload_frame(v, depth, color, mask_inout);
-		if (rc) return rc;
-		if (v->n_obs > 0) {
-			// tsdf.cu:426-461: back-project, fold, decide, relabel
-			rc = require_full_volume(v, "sfm_fuse_frame (merge)");
-			if (rc) return rc;
-			// everything up to the integration is enqueued without a host round trip: march, fold, decision
-			// and relabel on the device; the host only waits for the 2 KB report to relabel ITS copy of the
-			// mask, which overlaps the integrate kernels
-			// (K0 + K1a of this frame run on prep_stream meanwhile: they only need the uploaded images; the
-			// relabel waits for them because K0 range-checks the incoming labels)
-			rc = enqueue_prepare(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
-			if (rc) return rc;
-			rc = enqueue_march_fold(v, E16, v->d_mask);
-			if (rc) return rc;
-			CU(cudaStreamWaitEvent(v->stream, v->ctx[v->n_integrate % sfm_volume::kCtx].ev_ready, 0));
-			rc = enqueue_device_decision(v, v->d_fold, v->d_mask);
-			if (rc) return rc;
-			rc = enqueue_update(v, v->d_depth, v->d_rgb, v->d_mask, E16);
-			if (rc) return rc;
-			uint8_t lut[256];
-			rc = finish_device_decision(v, lut);
-			if (rc) return rc;
-			for (size_t i = 0; i < npx; i++) mask_inout[i] = lut[mask_inout[i]];  // tsdf.cu:372-389 does it in place
-		} else {
-			v->num_objs = mx + 1;  // tsdf.cu:464-467
-			rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
-			if (rc) return rc;
-		}
-	} else {
-		rc = upload_frame(v, depth, color, nullptr);
-		if (rc) return rc;
-		rc = integrate_device(v, v->d_depth, v->d_rgb, v->d_mask, E16, v->ev_uploaded[v->frame_cur]);
-		if (rc) return rc;
 	}
-	return release_frame(v);
+	int rc = upload_frame(v, depth, color, v->bins > 0 ? mask_inout : nullptr);
+	if (rc) return rc;
+	rc = fuse_uploaded_frame(v, mask_inout, mx, E16);
+	const std::string keep = g_err;
+	const int rc2 = release_frame(v);  // on every path: the buffer's consumed event must follow the work enqueued so far
+	if (rc) { g_err = keep; return rc; }
+	return rc2;
 }
 
 int sfm_parse_frame(sfm_volume *v, const uint16_t *depth, const uint8_t *color, uint8_t *mask_inout,
@@ -1521,6 +1592,20 @@ int sfm_synchronize(sfm_volume *v) {
 	if (!v) return fail(SFM_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(v->desc.device));
 	return check_device_error(v);
+}
+
+int sfm_wait_uploads(sfm_volume *v) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaStreamSynchronize(v->copy_stream));
+	return SFM_OK;
+}
+
+int sfm_planes_written(sfm_volume *v) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemsetAsync(v->planes.occ, 1, v->occ_bytes, v->stream));  // arbitrary SDF: no block may be skipped
+	return SFM_OK;
 }
 
 int sfm_set_stream(sfm_volume *v, void *cuda_stream) {

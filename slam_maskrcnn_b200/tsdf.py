@@ -279,6 +279,14 @@ class Volume:
     def synchronize(self):
         check(self.lib.sfm_synchronize(self._h))
 
+    def wait_uploads(self):
+        """Blocks until every frame copy issued so far has read its source buffers (FLAG_ASYNC_SOURCES)."""
+        check(self.lib.sfm_wait_uploads(self._h))
+
+    def planes_written(self):
+        """Tell the library the SDF plane was written through plane_ptr() (resets the surface-block map)."""
+        check(self.lib.sfm_planes_written(self._h))
+
     def set_stream(self, cuda_stream):
         check(self.lib.sfm_set_stream(self._h, C.c_void_p(cuda_stream)))
 

@@ -1,5 +1,5 @@
 """K1 A/B tool: one process, one 512^3 x 80-bin volume, the bench's frames resident in HBM; runs the
-integrate step under several SFM_DEBUG_ABLATE settings (read per launch by the library) and prints the
+integrate step under several SFM_DEBUG_ABLATE settings (one volume per setting) and prints the
 mean CUDA-event time of K1 for each.  `SFM_B200_LIB=<path>` selects another build of the library.
 
     python tools/k1_ablate.py [--dims 512 512 512] [--bins 80] [--steps 60] [--ablate 0 8 16 24]
@@ -40,11 +40,12 @@ def main():
     poses = [np.ascontiguousarray(fr["extrinsic"], dtype=np.float32) for fr in frames]
     out = {"lib": _lib.LIB_PATH, "dims": dims, "bins": args.bins, "runs": []}
     for flags in args.flags:
-        v = Volume(dims=dims, bins=args.bins, width=640, height=480, K=K, Kinv=Kinv, flags=flags,
-                   slab=tuple(args.slab) if args.slab else None)
-        v.set_bounds(*place)
         for ab in args.ablate:
+            # the library reads SFM_DEBUG_ABLATE once, at creation, and only under FLAG_DEBUG_ABLATE
             os.environ["SFM_DEBUG_ABLATE"] = str(ab)
+            v = Volume(dims=dims, bins=args.bins, width=640, height=480, K=K, Kinv=Kinv, flags=flags | _lib.FLAG_DEBUG_ABLATE,
+                       slab=tuple(args.slab) if args.slab else None)
+            v.set_bounds(*place)
             for i in range(5):
                 p = packed[i % len(packed)].data_ptr()
                 v.integrate_dev(p, p + npx * 2, p + npx * 5, poses[i % len(packed)], ready=READY)
@@ -71,7 +72,7 @@ def main():
                  "k1_ms_min": float(np.min(ms)), "step_wall_ms": wall_ms, "k1a_ms": float(np.mean(ms_a)), "k1b_ms": float(np.mean(ms_b)), "U_per_step": U / args.steps, "S_per_step": S / args.steps}
             out["runs"].append(r)
             print(json.dumps(r), flush=True)
-        v.close()
+            v.close()
     os.environ.pop("SFM_DEBUG_ABLATE", None)
     print(json.dumps(out))
 
