@@ -184,6 +184,14 @@ size_t sfm_plane_bytes(sfm_volume *v, int plane);
  * blocks that ever held a near-surface value and skips the others (sfm_upload does this itself). */
 void *sfm_plane_device_ptr(sfm_volume *v, int plane);
 int sfm_planes_written(sfm_volume *v);
+/* Histogram at the boundary vs inside.  sfm_download / sfm_upload / sfm_plane_bytes speak the reference's
+ * u32 hist[v*bins + label] (tsdf.cu:61, tsdf.cuh:26).  Inside, the plane is tiled along z and 16 bits wide (a bin
+ * counts frames, one vote per frame at most: 65535 labelled frames per volume, checked; the reference's own cap is
+ * 100 frames, kernel.cpp:60).  sfm_plane_device_ptr(SFM_PLANE_HIST) therefore returns a reference-layout device
+ * SNAPSHOT owned by the library and refreshed by every call (bins x 4 bytes per voxel of extra device memory);
+ * sfm_hist_export_dev writes the same into a caller-owned device buffer of sfm_plane_bytes(SFM_PLANE_HIST) bytes,
+ * ordered on the handle's stream. */
+int sfm_hist_export_dev(sfm_volume *v, void *d_dst_u32);
 /* Blocks until every frame copy issued so far has read its source buffers (see SFM_FLAG_ASYNC_SOURCES). */
 int sfm_wait_uploads(sfm_volume *v);
 

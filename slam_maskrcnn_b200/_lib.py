@@ -90,6 +90,7 @@ SYMBOLS = {
     "sfm_synchronize": (_i, [_vp]),
     "sfm_wait_uploads": (_i, [_vp]),
     "sfm_planes_written": (_i, [_vp]),
+    "sfm_hist_export_dev": (_i, [_vp, _vp]),
     "sfm_set_stream": (_i, [_vp, _vp]),
     "sfm_timer_start": (_i, [_vp]),
     "sfm_timer_stop": (_i, [_vp, C.POINTER(_f)]),

@@ -214,8 +214,8 @@ __device__ __forceinline__ int ld_u8_hint(const uint8_t *a, unsigned long long p
 __device__ __forceinline__ void st_u8_hint(uint8_t *a, int v, unsigned long long pol) {
 	asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void red_add_hint(uint32_t *a, unsigned long long pol) {
-	asm volatile("red.global.add.L2::cache_hint.u32 [%0], 1, %1;" ::"l"(a), "l"(pol) : "memory");
+__device__ __forceinline__ void red_add_hint(uint32_t *a, unsigned inc, unsigned long long pol) {
+	asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(inc), "l"(pol) : "memory");
 }
 
 constexpr int kQueue = 160;  // per-warp capacity of the deferred near-surface queue (one brick = 128 voxels, drained at >= 32)
@@ -226,7 +226,7 @@ constexpr int kQueue = 160;  // per-warp capacity of the deferred near-surface q
 // as a reduction (RED.ADD, no return value): the add happens in L2, the warp never waits for the bin's
 // sector to arrive from DRAM -- with a load / store pair every drain stalled on 32 random sectors.
 template <bool LABELS>
-__device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const FrameView &f, const uint4 *q, int count,
+__device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const VolGeom &g, const FrameView &f, const uint4 *q, int count,
 	int lane, uint32_t *err)
 {
 	__syncwarp();
@@ -235,8 +235,8 @@ __device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const Fram
 	for (int base = 0; base < count; base += 32) {
 		const int i = base + lane;
 		if (i < count) {
-			const uint4 e = q[i];
-			const size_t v = (size_t)e.x | ((size_t)e.y << 32);
+			const uint4 e = q[i];  // {column, local z, pixel, weight}
+			const size_t v = (size_t)e.x * (size_t)g.nz + e.y;
 			const int img = (int)e.z, w = (int)e.w;
 			const uint8_t *src = f.rgb + (size_t)img * 3;
 			uint8_t *dst = p.color + v * 3;
@@ -244,8 +244,12 @@ __device__ __noinline__ unsigned drain_surface_queue(const Planes &p, const Fram
 			const int c0 = ld_u8_hint(dst, keep), c1 = ld_u8_hint(dst + 1, keep), c2 = ld_u8_hint(dst + 2, keep);
 			if (LABELS) {
 				const unsigned label = __ldg(f.mask + img);
-				if ((int)label < p.bins) red_add_hint(p.hist + v * (size_t)p.bins + label, keep);
-				else atomicOr(err, 1u);
+				if ((int)label < p.bins) {
+					// 16-bit bin inside an aligned 32-bit word: add 1 to its half (no carry: a bin never exceeds the
+					// number of frames, which the host caps at 65535)
+					const size_t hi = hist_index(e.x, (int)e.y, g.ngz, p.bins, (int)label);
+					red_add_hint(reinterpret_cast<uint32_t *>(p.hist + (hi & ~(size_t)1)), (hi & 1) ? 0x10000u : 1u, keep);
+				} else atomicOr(err, 1u);
 			}
 			st_u8_hint(dst, (c0 * w + s0) / (w + 1), keep);
 			st_u8_hint(dst + 1, (c1 * w + s1) / (w + 1), keep);
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(kK1aThreads) quad_kernel(VolGeom g, FrameView 
 	const int csh = zsh + (VEC4 ? 2 : 0);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int zq = lane & ((1 << zsh) - 1), ci = lane >> zsh;
-	extern __shared__ __align__(16) unsigned char smem_dyn[];
+	extern __shared__ __align__(128) unsigned char smem_dyn[];
 	uint2 *s_bk = reinterpret_cast<uint2 *>(smem_dyn) + (size_t)warp * (kStageB + kStageX);
 	uint2 *s_xq = s_bk + kStageB;
 	int nbk = 0, nxq = 0;  // warp-uniform
@@ -708,7 +712,7 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 	const int zq = lane & ((1 << zsh) - 1), ci = lane >> zsh;
 	const size_t lane_off = (size_t)ci * (size_t)g.nz + (size_t)(zq * VEC);  // lane's quad relative to the brick's first voxel
 	unsigned nU = 0, nS = 0;
-	// dynamic shared memory: per warp, kQueue deferred near-surface voxels {voxel lo, hi, pixel, weight}
+	// dynamic shared memory: per warp, kQueue deferred near-surface voxels {column, local z, pixel, weight}
 	extern __shared__ __align__(128) unsigned char smem_dyn[];
 	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
 	int qcount = 0;  // warp-uniform
@@ -821,7 +825,7 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		// histogram sectors requested with prefetch.global.L2 -- during an earlier evaluation, so
 		// the drain's dependent loads hit L2 instead of waiting for DRAM one after another.
 		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another 32 x VEC voxels: drain
-			nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
+			nS += drain_surface_queue<LABELS>(p, g, f, q, qcount, lane, err);
 			qcount = 0;
 		}
 		if (__any_sync(0xffffffffu, surface != 0)) {
@@ -858,9 +862,8 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 				const unsigned m = __ballot_sync(0xffffffffu, sf);
 				if (sf) {
 					const int slot = qcount + __popc(m & ((1u << lane) - 1u));
-					const unsigned long long vv = (unsigned long long)(v0 + k);
-					q[slot] = make_uint4((unsigned)vv, (unsigned)(vv >> 32), (unsigned)img[k], (unsigned)w[k]);
-					if (!(f.debug & 16)) prefetch_l2_keep(p.color + vv * 3);  // (the histogram bin is updated by a reduction in L2)
+					q[slot] = make_uint4((unsigned)x * (unsigned)g.Dy + (unsigned)y, (unsigned)(zl + k), (unsigned)img[k], (unsigned)w[k]);
+					if (!(f.debug & 16)) prefetch_l2_keep(p.color + (v0 + k) * 3);  // (the histogram bin is updated by a reduction in L2)
 				}
 				qcount += __popc(m);
 			}
@@ -976,7 +979,7 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		pass += nwarps;
 		grp += nwarps;
 	}
-	if (qcount) nS += drain_surface_queue<LABELS>(p, f, q, qcount, lane, err);
+	if (qcount) nS += drain_surface_queue<LABELS>(p, g, f, q, qcount, lane, err);
 
 	// fold U / S: warp shuffle, then one spread atomic pair per warp (no block barrier: warps with
 	// little work must not hold their slot waiting for the busiest warp of the block)

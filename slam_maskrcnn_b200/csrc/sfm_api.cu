@@ -176,6 +176,12 @@ struct sfm_volume {
 	// per-handle (= per-device) launch state: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
 	size_t k1a_smem_set = 0;   // dynamic shared memory K1a has been configured for on this handle's device
 	int k1b_per_sm[8] = {};    // resident K1b blocks per SM, per kernel instantiation (0 = not queried yet)
+	// histogram: tiled 16-bit plane inside (sfm_device.cuh), reference layout at the boundary
+	size_t hist_elems = 0;       // hist_t entries of the tiled plane
+	uint32_t *d_hist_ref = nullptr;  // lazily allocated reference-layout mirror behind sfm_plane_device_ptr(HIST)
+	uint32_t *d_hist_chunk = nullptr; // staging for sfm_download / sfm_upload (kHistChunk bytes)
+	unsigned *d_hist_max = nullptr;
+	uint32_t hist_bound = 0;     // upper bound of every bin: frames integrated (+ the largest uploaded value)
 	int k1q_blocks_per_sm = 8; // grid of quad_kernel (K1a pass 3), blocks per SM
 	int debug_ablate = 0;      // SFM_DEBUG_ABLATE, read once at creation and only under SFM_FLAG_DEBUG_ABLATE
 };
@@ -207,8 +213,7 @@ void *plane_ptr(const sfm_volume *v, int plane) {
 	case SFM_PLANE_SDF: return v->planes.sdf;
 	case SFM_PLANE_WEIGHT: return v->planes.wt;
 	case SFM_PLANE_COLOR: return v->planes.color;
-	case SFM_PLANE_HIST: return v->planes.hist;
-	default: return nullptr;
+	default: return nullptr;  // the histogram is stored tiled: see hist_export / sfm_plane_device_ptr
 	}
 }
 
@@ -218,7 +223,8 @@ int reset_planes(sfm_volume *v) {
 	LAUNCH_CHECK(v);
 	CU(cudaMemsetAsync(v->planes.wt, 0, v->nvox * 4, v->stream));
 	CU(cudaMemsetAsync(v->planes.color, 0, v->nvox * 3, v->stream));
-	if (v->bins > 0) CU(cudaMemsetAsync(v->planes.hist, 0, v->nvox * 4 * (size_t)v->bins, v->stream));
+	if (v->bins > 0) CU(cudaMemsetAsync(v->planes.hist, 0, v->hist_elems * sizeof(hist_t), v->stream));
+	v->hist_bound = 0;
 	CU(cudaMemsetAsync(v->planes.occ, 0, v->occ_bytes, v->stream));
 	v->n_obs = 0;
 	v->num_objs = 0;
@@ -462,6 +468,8 @@ int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const 
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	const WorkLists wl{c.d_list_mixed, c.d_list_bricks, c.d_list_exact, c.d_work};
+	if (v->bins > 0 && v->hist_bound >= 65535u)
+		return fail(SFM_ERR_INVALID, "the histogram bins are 16 bits wide inside the library: at most 65535 labelled frames per volume");
 	CU(cudaStreamWaitEvent(v->stream, c.ev_ready, 0));
 	CU(cudaEventRecord(v->ev_kb[slot], v->stream));
 	if (vec4) {
@@ -475,6 +483,7 @@ int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const 
 	CU(cudaEventRecord(v->ev_k1[slot], v->stream));
 	CU(cudaEventRecord(c.ev_free, v->stream));
 	v->n_integrate++;
+	if (v->bins > 0) v->hist_bound++;
 	v->n_obs++;  // tsdf.cu:220 (counted here so the raw / device entry points keep n_obs consistent)
 	if (v->desc.flags & SFM_FLAG_SYNC_EVERY_CALL) CU(cudaStreamSynchronize(v->stream));
 	return SFM_OK;
@@ -951,7 +960,12 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
 	CU_OR_DESTROY(cudaMalloc(&v->planes.wt, v->nvox * 4));
 	CU_OR_DESTROY(cudaMalloc(&v->planes.color, v->nvox * 3));
-	if (v->bins > 0) CU_OR_DESTROY(cudaMalloc(&v->planes.hist, v->nvox * 4 * (size_t)v->bins));
+	v->g.ngz = (v->g.nz + kHistTZ - 1) / kHistTZ;
+	v->hist_elems = (size_t)v->g.Dx * v->g.Dy * v->g.ngz * (size_t)std::max(v->bins, 0) * kHistTZ;
+	if (v->bins > 0) {
+		CU_OR_DESTROY(cudaMalloc(&v->planes.hist, v->hist_elems * sizeof(hist_t)));
+		CU_OR_DESTROY(cudaMalloc(&v->d_hist_max, 4));
+	}
 	v->planes.bins = v->bins;
 	{  // surface-block map, see Planes::occ
 		const int obx = (v->g.Dx + 7) / 8;
@@ -1065,6 +1079,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->prep_stream) cudaStreamSynchronize(v->prep_stream);
 	if (v->stream) cudaStreamSynchronize(v->stream);
 	cudaFree(v->planes.sdf); cudaFree(v->planes.wt); cudaFree(v->planes.color); cudaFree(v->planes.hist); cudaFree(v->planes.occ);
+	cudaFree(v->d_hist_ref); cudaFree(v->d_hist_chunk); cudaFree(v->d_hist_max);
 	if (v->copy_stream) cudaStreamSynchronize(v->copy_stream);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(v->d_frame[i]);
@@ -1548,14 +1563,64 @@ int sfm_show_color(sfm_volume *v, float angle, float dist, int w, int h, uint8_t
 }
 
 size_t sfm_plane_bytes(sfm_volume *v, int plane) { return v ? v->nvox * plane_elem_bytes(v, plane) : 0; }
-void *sfm_plane_device_ptr(sfm_volume *v, int plane) { return v ? plane_ptr(v, plane) : nullptr; }
+
+namespace {
+constexpr size_t kHistChunk = 256u << 20;  // staging bytes for histogram transfers (reference layout)
+
+// reference-layout u32 histogram of voxels [v0, v1) into / from a device buffer
+int hist_export(sfm_volume *v, size_t v0, size_t v1, uint32_t *d_ref) {
+	hist_export_kernel<<<v->num_sms * 16, 256, 0, v->stream>>>(v->planes.hist, v->g.nz, v->g.ngz, v->bins, v0, v1, d_ref);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+int hist_import(sfm_volume *v, size_t v0, size_t v1, const uint32_t *d_ref) {
+	hist_import_kernel<<<v->num_sms * 16, 256, 0, v->stream>>>(v->planes.hist, v->g.nz, v->g.ngz, v->bins, v0, v1, d_ref, v->d_hist_max);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+}  // namespace
+
+void *sfm_plane_device_ptr(sfm_volume *v, int plane) {
+	if (!v) return nullptr;
+	if (plane != SFM_PLANE_HIST) return plane_ptr(v, plane);
+	// the reference exposes tsdf_cnt_d (tsdf.cuh:26); the library's own plane is tiled and 16 bits wide, so this
+	// returns a reference-layout SNAPSHOT (u32[v*bins + label]) refreshed by every call
+	if (v->bins <= 0 || cudaSetDevice(v->desc.device) != cudaSuccess) return nullptr;
+	if (!v->d_hist_ref && cudaMalloc(&v->d_hist_ref, v->nvox * 4 * (size_t)v->bins) != cudaSuccess) {
+		cudaGetLastError();
+		fail(SFM_ERR_NOMEM, "no memory for the reference-layout histogram snapshot");
+		return nullptr;
+	}
+	if (hist_export(v, 0, v->nvox, v->d_hist_ref) != SFM_OK || cudaStreamSynchronize(v->stream) != cudaSuccess) return nullptr;
+	return v->d_hist_ref;
+}
+
+int sfm_hist_export_dev(sfm_volume *v, void *d_dst_u32) {
+	if (!v || !d_dst_u32) return fail(SFM_ERR_INVALID, "null argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	CU(cudaSetDevice(v->desc.device));
+	return hist_export(v, 0, v->nvox, (uint32_t *)d_dst_u32);
+}
 
 int sfm_download(sfm_volume *v, int plane, void *dst, size_t bytes) {
 	if (!v || !dst) return fail(SFM_ERR_INVALID, "null argument");
 	const size_t need = sfm_plane_bytes(v, plane);
 	if (!need || bytes != need) return fail(SFM_ERR_INVALID, "plane / size mismatch");
 	CU(cudaSetDevice(v->desc.device));
-	CU(cudaMemcpyAsync(dst, plane_ptr(v, plane), need, cudaMemcpyDeviceToHost, v->stream));
+	if (plane != SFM_PLANE_HIST) {
+		CU(cudaMemcpyAsync(dst, plane_ptr(v, plane), need, cudaMemcpyDeviceToHost, v->stream));
+		return check_device_error(v);
+	}
+	// histogram: re-emit the reference layout and type (u32[v*bins + label]) chunk by chunk
+	if (!v->d_hist_chunk) CU(cudaMalloc(&v->d_hist_chunk, kHistChunk));
+	const size_t per_vox = 4 * (size_t)v->bins, vox_per_chunk = std::max<size_t>(1, kHistChunk / per_vox);
+	for (size_t v0 = 0; v0 < v->nvox; v0 += vox_per_chunk) {
+		const size_t v1 = std::min(v->nvox, v0 + vox_per_chunk);
+		int rc = hist_export(v, v0, v1, v->d_hist_chunk);
+		if (rc) return rc;
+		CU(cudaMemcpyAsync((uint8_t *)dst + v0 * per_vox, v->d_hist_chunk, (v1 - v0) * per_vox, cudaMemcpyDeviceToHost, v->stream));
+		CU(cudaStreamSynchronize(v->stream));
+	}
 	return check_device_error(v);
 }
 
@@ -1564,9 +1629,26 @@ int sfm_upload(sfm_volume *v, int plane, const void *src, size_t bytes) {
 	const size_t need = sfm_plane_bytes(v, plane);
 	if (!need || bytes != need) return fail(SFM_ERR_INVALID, "plane / size mismatch");
 	CU(cudaSetDevice(v->desc.device));
-	CU(cudaMemcpyAsync(plane_ptr(v, plane), src, need, cudaMemcpyHostToDevice, v->stream));
-	if (plane == SFM_PLANE_SDF) CU(cudaMemsetAsync(v->planes.occ, 1, v->occ_bytes, v->stream));  // arbitrary SDF: no block may be skipped
-	CU(cudaStreamSynchronize(v->stream));
+	if (plane != SFM_PLANE_HIST) {
+		CU(cudaMemcpyAsync(plane_ptr(v, plane), src, need, cudaMemcpyHostToDevice, v->stream));
+		if (plane == SFM_PLANE_SDF) CU(cudaMemsetAsync(v->planes.occ, 1, v->occ_bytes, v->stream));  // arbitrary SDF: no block may be skipped
+		CU(cudaStreamSynchronize(v->stream));
+		return SFM_OK;
+	}
+	if (!v->d_hist_chunk) CU(cudaMalloc(&v->d_hist_chunk, kHistChunk));
+	CU(cudaMemsetAsync(v->d_hist_max, 0, 4, v->stream));
+	const size_t per_vox = 4 * (size_t)v->bins, vox_per_chunk = std::max<size_t>(1, kHistChunk / per_vox);
+	for (size_t v0 = 0; v0 < v->nvox; v0 += vox_per_chunk) {
+		const size_t v1 = std::min(v->nvox, v0 + vox_per_chunk);
+		CU(cudaMemcpyAsync(v->d_hist_chunk, (const uint8_t *)src + v0 * per_vox, (v1 - v0) * per_vox, cudaMemcpyHostToDevice, v->stream));
+		int rc = hist_import(v, v0, v1, v->d_hist_chunk);
+		if (rc) return rc;
+		CU(cudaStreamSynchronize(v->stream));
+	}
+	unsigned mx = 0;
+	CU(cudaMemcpy(&mx, v->d_hist_max, 4, cudaMemcpyDeviceToHost));
+	v->hist_bound = std::min(mx, 65535u);
+	if (mx > 65535u) return fail(SFM_ERR_INVALID, "uploaded histogram holds a count above 65535 (16-bit bins inside the library); it was clamped");
 	return SFM_OK;
 }
 

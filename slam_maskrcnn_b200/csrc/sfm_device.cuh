@@ -14,6 +14,22 @@ constexpr int kTile = 8;           // depth tile edge (pixels) of the per-frame 
 constexpr int kStatSlots = 256;    // spread slots for the per-frame U/S counters
 constexpr int kMaxBins = 255;
 
+// Internal histogram layout.  The reference stores u32 hist[v*L + label] (tsdf.cu:61): one 4-byte bin per 32-byte
+// sector, and the ~10 near-surface voxels of a column (consecutive z) that a frame updates for the same label lie
+// 10 sectors -- 10 DRAM row activations -- apart.  Here a column is cut into groups of kHistTZ planes and the bins of
+// a group are stored bin-major, 16 bits each:
+//     hist[((col*ngz + z/TZ)*L + label)*TZ + z%TZ],   col = x*Dy + y,   ngz = ceil(nz/TZ)
+// so the same run of 10 voxels touches 3-4 sectors, the 8-tap gathers of the ray kernels read the same number of
+// bytes as before (a z, z+1 pair of taps shares an 8-byte unit three times out of four), and the plane is half the
+// size (512^3 x 80 bins: 21.5 GB).  A bin counts the frames that voted for it, at most one per frame, so 16 bits hold
+// 65535 frames (enforced by the host; the reference's own frame cap is 100, kernel.cpp:60).  sfm_download / sfm_upload
+// / sfm_plane_device_ptr convert to and from the reference layout and type.
+typedef uint16_t hist_t;
+constexpr int kHistTZ = 4;
+__host__ __device__ __forceinline__ size_t hist_index(size_t col, int zl, int ngz, int bins, int label) {
+	return ((col * (size_t)ngz + (size_t)(zl / kHistTZ)) * (size_t)bins + (size_t)label) * kHistTZ + (size_t)(zl % kHistTZ);
+}
+
 struct VolGeom {
 	int Dx, Dy, Dz;  // global volume dimensions (vol_dim_, tsdf.cuh:52)
 	int z0, nz;      // z-slab stored by this handle: global planes [z0, z0+nz)
@@ -25,6 +41,7 @@ struct VolGeom {
 	int oby, obz;         // strides of the 8x8x8 surface-block map (see Planes::occ)
 	int oby2, obz2;       // strides of the coarse 32x32x32 level of the same map
 	unsigned occ2_off;    // byte offset of the coarse level inside the map allocation
+	int ngz;      // z groups per column of the tiled histogram: ceil(nz / kHistTZ)
 	int zl_log2;  // K1 brick shape on the 128-bit path: 2^zl_log2 lanes (4 voxels each) along z per column, i.e. a
 	              // brick is (32 >> zl_log2) columns x (4 << zl_log2) planes; 3 = 4 columns x 32 planes.  Thin z-slabs
 	              // (a rank that owns only the planes around a fronto-parallel wall) use flatter bricks.
@@ -35,7 +52,7 @@ struct Planes {
 	float *sdf;
 	int32_t *wt;
 	uint8_t *color;
-	uint32_t *hist;
+	hist_t *hist;  // tiled, see hist_index()
 	int bins;
 	// Surface-block map: one byte per 8x8x8 block of voxels, set (never cleared) when a voxel of the
 	// block -- or a voxel one step beyond its low faces, i.e. a trilinear tap of a sample whose floor
