@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kK1aThreads) quad_kernel(VolGeom g, FrameView 
 	const unsigned below = (1u << lane) - 1u;
 	// dynamic distribution (kQuadGrab bricks per atomic): this kernel runs next to a resident wave of K1b, so only some of
 	// its blocks are on the machine at any time and a static split would leave work to blocks that start late
-	constexpr unsigned kQuadGrab = 8;
+	constexpr unsigned kQuadGrab = 16;
 	for (;;) {
 	unsigned i0 = 0;
 	if (lane == 0) i0 = atomicAdd(wl.counts + 3, kQuadGrab);

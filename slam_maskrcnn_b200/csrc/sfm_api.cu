@@ -170,6 +170,7 @@ struct sfm_volume {
 	static constexpr int kRing = 2048;  // per-call event pairs around K1 (integrate kernel only)
 	cudaEvent_t ev_k0[kRing] = {}, ev_km[kRing] = {};  // around K1a (prep_stream)
 	cudaEvent_t ev_kb[kRing] = {}, ev_k1[kRing] = {};  // around K1b (main stream)
+	cudaEvent_t ev_kq[kRing] = {};                      // before K1a pass 3 (main stream; it ends where K1b begins)
 	uint64_t n_integrate = 0;
 	uint64_t launches = 0;
 	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
@@ -182,7 +183,7 @@ struct sfm_volume {
 	uint32_t *d_hist_chunk = nullptr; // staging for sfm_download / sfm_upload (kHistChunk bytes)
 	unsigned *d_hist_max = nullptr;
 	uint32_t hist_bound = 0;     // upper bound of every bin: frames integrated (+ the largest uploaded value)
-	int k1q_blocks_per_sm = 8; // grid of quad_kernel (K1a pass 3), blocks per SM
+	int k1q_blocks_per_sm = 16; // grid of quad_kernel (K1a pass 3), blocks per SM
 	int debug_ablate = 0;      // SFM_DEBUG_ABLATE, read once at creation and only under SFM_FLAG_DEBUG_ABLATE
 };
 
@@ -368,8 +369,8 @@ void launch_quads(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
 	const bool quads = VEC4 && canonical_k(v, f) && !(v->desc.flags & SFM_FLAG_NO_QUADS);
 	const size_t smem = (size_t)(kK1aThreads / 32) * (kStageB + kStageX) * sizeof(uint2);
 	const int blocks = v->num_sms * v->k1q_blocks_per_sm;
-	if (quads) quad_kernel<VEC4, VEC4><<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
-	else quad_kernel<VEC4, false><<<blocks, kK1aThreads, smem, v->prep_stream>>>(v->g, f, wl);
+	if (quads) quad_kernel<VEC4, VEC4><<<blocks, kK1aThreads, smem, v->stream>>>(v->g, f, wl);
+	else quad_kernel<VEC4, false><<<blocks, kK1aThreads, smem, v->stream>>>(v->g, f, wl);
 }
 
 // K1b: update of the listed bricks
@@ -453,9 +454,7 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 	if (vec4) launch_classify<true>(v, f, wl, nsb);
 	else launch_classify<false>(v, f, wl, nsb);
 	LAUNCH_CHECK(v);
-	if (vec4) launch_quads<true>(v, f, wl);
-	else launch_quads<false>(v, f, wl);
-	LAUNCH_CHECK(v);
+
 	CU(cudaEventRecord(v->ev_km[slot], v->prep_stream));
 	CU(cudaEventRecord(c.ev_ready, v->prep_stream));
 	return SFM_OK;
@@ -471,6 +470,13 @@ int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const 
 	if (v->bins > 0 && v->hist_bound >= 65535u)
 		return fail(SFM_ERR_INVALID, "the histogram bins are 16 bits wide inside the library: at most 65535 labelled frames per volume");
 	CU(cudaStreamWaitEvent(v->stream, c.ev_ready, 0));
+	// K1a pass 3 (quads of the MIXED bricks) runs on the MAIN stream, between the previous frame's update and this
+	// one: it needs the whole machine for ~30 us; next to a resident wave of K1b (prep_stream, like passes 1 + 2) it got
+	// one block per SM and held the next update back for longer than that (measured: step 0.173 vs 0.16 ms)
+	CU(cudaEventRecord(v->ev_kq[slot], v->stream));
+	if (vec4) launch_quads<true>(v, f, wl);
+	else launch_quads<false>(v, f, wl);
+	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_kb[slot], v->stream));
 	if (vec4) {
 		if (v->bins > 0) launch_update<4, true>(v, f, wl, gate);
@@ -955,6 +961,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k0[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_km[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_kb[i]));
+		CU_OR_DESTROY(cudaEventCreate(&v->ev_kq[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k1[i]));
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
@@ -1116,6 +1123,7 @@ void sfm_destroy(sfm_volume *v) {
 		if (v->ev_k0[i]) cudaEventDestroy(v->ev_k0[i]);
 		if (v->ev_km[i]) cudaEventDestroy(v->ev_km[i]);
 		if (v->ev_kb[i]) cudaEventDestroy(v->ev_kb[i]);
+		if (v->ev_kq[i]) cudaEventDestroy(v->ev_kq[i]);
 		if (v->ev_k1[i]) cudaEventDestroy(v->ev_k1[i]);
 	}
 	if (v->own_stream && v->stream) cudaStreamDestroy(v->stream);
@@ -1722,9 +1730,9 @@ int sfm_integrate_times(sfm_volume *v, float *ms, int n) {
 	for (int i = 0; i < n; i++) {
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
-		float a = 0.f, b = 0.f;  // K1a (prep_stream) + K1b (main stream): the two may overlap other frames' kernels
+		float a = 0.f, b = 0.f;  // K1a passes 1 + 2 (prep_stream) + pass 3 and K1b (main stream)
 		CU(cudaEventElapsedTime(&a, v->ev_k0[slot], v->ev_km[slot]));
-		CU(cudaEventElapsedTime(&b, v->ev_kb[slot], v->ev_k1[slot]));
+		CU(cudaEventElapsedTime(&b, v->ev_kq[slot], v->ev_k1[slot]));
 		ms[i] = a + b;
 	}
 	return SFM_OK;
@@ -1738,7 +1746,10 @@ int sfm_integrate_times2(sfm_volume *v, float *ms_classify, float *ms_update, in
 	for (int i = 0; i < n; i++) {
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
-		CU(cudaEventElapsedTime(ms_classify + i, v->ev_k0[slot], v->ev_km[slot]));
+		float a = 0.f, q = 0.f;
+		CU(cudaEventElapsedTime(&a, v->ev_k0[slot], v->ev_km[slot]));
+		CU(cudaEventElapsedTime(&q, v->ev_kq[slot], v->ev_kb[slot]));
+		ms_classify[i] = a + q;  // K1a passes 1 + 2 (prep stream, overlapped) + pass 3 (main stream)
 		CU(cudaEventElapsedTime(ms_update + i, v->ev_kb[slot], v->ev_k1[slot]));
 	}
 	return SFM_OK;
