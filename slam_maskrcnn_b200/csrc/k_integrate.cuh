@@ -863,7 +863,16 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 				if (sf) {
 					const int slot = qcount + __popc(m & ((1u << lane) - 1u));
 					q[slot] = make_uint4((unsigned)x * (unsigned)g.Dy + (unsigned)y, (unsigned)(zl + k), (unsigned)img[k], (unsigned)w[k]);
-					if (!(f.debug & 16)) prefetch_l2_keep(p.color + (v0 + k) * 3);  // (the histogram bin is updated by a reduction in L2)
+					if (!(f.debug & 16)) {
+						// colour and histogram sectors are requested now and touched by the drain one evaluation later: the
+						// drain's loads hit L2, and its reductions find their sector resident (a RED into a sector that is
+						// still in DRAM occupies the L2's atomic unit until the fill arrives and backs up into the SMs)
+						prefetch_l2_keep(p.color + (v0 + k) * 3);
+						if (LABELS) {
+							const unsigned label = __ldg(f.mask + img[k]);
+							if ((int)label < p.bins) prefetch_l2_keep(p.hist + hist_index((size_t)x * g.Dy + y, zl + k, g.ngz, p.bins, (int)label));
+						}
+					}
 				}
 				qcount += __popc(m);
 			}
