@@ -53,8 +53,6 @@ enum {
 	SFM_FLAG_SYNC_EVERY_CALL = 4, /* cudaStreamSynchronize before returning from every call        */
 	SFM_FLAG_GENERIC_K = 8,    /* evaluate K*c with all nine terms even when K has the pinhole zero pattern
 	                              (the default drops the exact-zero terms; same results)                  */
-	SFM_FLAG_NO_QUADS = 16,    /* send every quad (4 z voxels of a column) of a listed brick through the exact
-	                              per-voxel path instead of classifying quads first (same results)        */
 	SFM_FLAG_DEBUG_ABLATE = 32, /* profiling builds only: honour the SFM_DEBUG_ABLATE environment variable
 	                              (switches parts of the integrate kernel OFF; results are then wrong)    */
 	SFM_FLAG_ASYNC_SOURCES = 64 /* pinned-host / device frame buffers passed to sfm_integrate_raw,

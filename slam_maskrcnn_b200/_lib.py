@@ -50,7 +50,6 @@ FLAG_NO_CULL = 1
 FLAG_NO_TMA = 2
 FLAG_GENERIC_K = 8
 FLAG_SYNC_EVERY_CALL = 4
-FLAG_NO_QUADS = 16
 FLAG_DEBUG_ABLATE = 32
 FLAG_ASYNC_SOURCES = 64
 PLANE_SDF, PLANE_WEIGHT, PLANE_COLOR, PLANE_HIST = 0, 1, 2, 3

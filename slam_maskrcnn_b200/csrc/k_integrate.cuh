@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const uint16_t *__restr
 	uint32_t *__restrict__ err, unsigned *__restrict__ work_counter)
 {
 	const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gtid < 8) work_counter[gtid] = 0u;  // WorkLists::counts: list sizes
+	if (gtid < 3) work_counter[gtid] = 0u;  // WorkLists::counts: list sizes and K1b's fetch cursor
 	const int warp = gtid >> 5, lane = threadIdx.x & 31;
 	if (warp >= TW * TH) return;
 	const int ty = warp / TW, tx = warp % TW;
@@ -131,7 +131,7 @@ enum BrickClass { kCull = 0, kMixed = 1, kFree = 2 };
 #define SFM_K1_THREADS 128  // threads per K1b block (7 resident blocks per SM leave room for one K1a block)
 #endif
 #ifndef SFM_K1_MIN_BLOCKS
-#define SFM_K1_MIN_BLOCKS 7  // resident blocks per SM K1b is compiled for (register cap 72)
+#define SFM_K1_MIN_BLOCKS (1024 / SFM_K1_THREADS)  // resident blocks per SM K1b is compiled for (register cap 64)
 #endif
 constexpr int kK1Threads = SFM_K1_THREADS;
 
@@ -375,100 +375,29 @@ __device__ __forceinline__ int classify_box_lane(const FrameView &f, const VolGe
 	return classify_bounds(f, g, tilemax, tilemin, b, 160);
 }
 
-// Work lists written by K1a and consumed by K1b.  A brick id packs (x, brick row, z chunk).
+// Brick work lists written by K1a and consumed by K1b.  A brick id packs (x, brick row, z chunk).
 struct WorkLists {
-	uint32_t *mixed;    // K1a pass 2 -> pass 3: ids of the bricks that need a per-quad look
-	uint2 *bricks;      // {id, free mask}: bit l of the mask = lane l's quad of the brick (column l >> zsh, planes
-	                    // VEC*(l & (2^zsh - 1)) ..) is FREE: every voxel of the quad gets diff == 1.0f
-	uint2 *exact;       // EXACT quads {x | y << 16, local z of the first voxel}: K1b evaluates 32 of them per warp pass
-	unsigned *counts;   // [0] = #brick entries, [1] = #exact quads, [2] = #mixed ids, [3] = pass 3's cursor   (8 words, zeroed by K0)
+	uint32_t *mixed;   // bricks that need per-voxel evaluation
+	uint32_t *free_;   // bricks whose voxels all get diff == 1.0f
+	unsigned *counts;  // [0] = #mixed, [1] = #free, [2] = K1b's fetch cursor   (zeroed by K0)
 };
 constexpr int kIdXShift = 21, kIdGShift = 10;  // id = x << 21 | row << 10 | chunk  (x, row < 2048, chunk < 1024)
 #ifndef SFM_K1_FETCH
 #define SFM_K1_FETCH 4
 #endif
-constexpr int kFetch = SFM_K1_FETCH;           // bricks per K1b work item
+constexpr int kFetch = SFM_K1_FETCH;           // bricks a K1b warp takes per fetch
+#ifndef SFM_K1_PERMUTE
+#define SFM_K1_PERMUTE 1
+#endif
 
 constexpr int kK1aThreads = 128;               // K1a block size: small enough to run next to a resident wave of K1b
 constexpr int kSbPerBlock = 64;                // most super-blocks one K1a block classifies (sizes its shared lists)
-constexpr int kStageB = 64, kStageX = 256;     // pass 3: per-warp staging of brick entries / exact quads (one atomic per flush)
-
-constexpr int kWin = 8;                        // edge of K0b's depth-range windows (pixels)
-
-// Quad classification (K1a, pass 3).  A quad = the VEC consecutive z voxels (x, y, zl .. zl+VEC-1) one K1b lane owns.
-//     0 SKIP   all voxels provably fail the reference's tests (pixel outside the image, only invalid depth in the
-//              window, or behind the surface band: tsdf.cu:46-50);
-//     1 FREE   all provably project inside the image onto valid pixels in front of the band: diff clamps to miu,
-//              i.e. the update is weight += 1, sdf = (sdf*w + 1)/(w + 1);
-//     2 EXACT  anything else: per-voxel evaluation with the reference's op order.
-// Both END voxels are projected with the reference's own operation order (their camera-space positions are the exact
-// values the per-voxel path computes); the voxels between them lie, in exact arithmetic, on the segment between
-// the ends, which a projective map with all depths on one side of the camera plane sends to the segment between the
-// projected ends.  Rounding: every computed camera coordinate is within dc = 2.5e-7*scale of its exact value
-// (4 roundings of relative 6e-8 on terms bounded by scale, as in classify_bounds); a pixel coordinate
-// q = (c*.K0 + cz.K2)/cz then moves by at most (kx + |q|)*dc/cz + 2e-7*(kx + |q|); the slack below is 16x / 10x that,
-// and the depth comparisons carry eps = 1e-4*(scale + depth) like the brick test.  One look-up in the windowed
-// depth-range image (K0b) bounds the depth of every pixel the quad can land on.  Pinhole K only (sz == cz).
-// Straight-line code (the look-up is unconditional, at a clamped address) so that two quads interleave.
-template <int VEC>
-__device__ __forceinline__ int classify_quad(const FrameView &f, const VolGeom &g, int x, int y, int zl)
-{
-	const float px = __fmaf_rn((float)x, g.vx, g.sx);
-	const float py = __fmaf_rn((float)y, g.vy, g.sy);
-	const float h0 = affine_hoist(px, py, f.E[0], f.E[1]);
-	const float h1 = affine_hoist(px, py, f.E[4], f.E[5]);
-	const float h2 = affine_hoist(px, py, f.E[8], f.E[9]);
-	const float pza = __fmaf_rn((float)(g.z0 + zl), g.vz, g.sz), pzb = __fmaf_rn((float)(g.z0 + zl + VEC - 1), g.vz, g.sz);
-	const float cxa = affine_finish(h0, pza, f.E[2], f.E[3]), cxb = affine_finish(h0, pzb, f.E[2], f.E[3]);
-	const float cya = affine_finish(h1, pza, f.E[6], f.E[7]), cyb = affine_finish(h1, pzb, f.E[6], f.E[7]);
-	const float cza = affine_finish(h2, pza, f.E[10], f.E[11]), czb = affine_finish(h2, pzb, f.E[10], f.E[11]);
-	const float czmin = fminf(cza, czb), czmax = fmaxf(cza, czb);
-	const float scale = f.cull_scale;  // bound of |camera coordinates| over the whole volume
-	float ra, rb;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(cza));
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(czb));
-	const float ua = __fmaf_rn(cxa * f.K[0], ra, f.K[2]), ub = __fmaf_rn(cxb * f.K[0], rb, f.K[2]);
-	const float va = __fmaf_rn(cya * f.K[4], ra, f.K[5]), vb = __fmaf_rn(cyb * f.K[4], rb, f.K[5]);
-	const float umin = fminf(ua, ub), umax = fmaxf(ua, ub), vmin = fminf(va, vb), vmax = fmaxf(va, vb);
-	const float rel = __fmaf_rn(4e-6f * scale, fmaxf(ra, rb), 2e-6f);  // 16 x dc / czmin + 10 x 2e-7
-	const float su = rel * (f.cull_kx + fmaxf(fabsf(umin), fabsf(umax)));
-	const float sw = rel * (f.cull_ky + fmaxf(fabsf(vmin), fabsf(vmax)));
-	// all voxels in front of the camera plane by a margin (NaNs fail), pixel coordinates sane
-	const bool front = czmin > 1e-2f * scale && fmaxf(fabsf(umin), fabsf(umax)) < 1e6f && fmaxf(fabsf(vmin), fabsf(vmax)) < 1e6f;
-	const int xlo = __float2int_rd(umin - su), xhi = __float2int_rd(umax + su);
-	const int ylo = __float2int_rd(vmin - sw), yhi = __float2int_rd(vmax + sw);
-	const bool outside = xhi < 0 || xlo >= f.W || yhi < 0 || ylo >= f.H;  // every voxel projects outside the image
-	const bool inside = xlo >= 0 && xhi < f.W && ylo >= 0 && yhi < f.H;
-	const int ax = min(max(xlo, 0), f.W - 1), ay = min(max(ylo, 0), f.H - 1);
-	const bool fits = min(xhi, f.W - 1) - ax < kWin && min(yhi, f.H - 1) - ay < kWin;  // the window covers the rectangle
-	const float2 wd = __ldg(f.win + (size_t)ay * f.W + ax);
-	const float eps = 1e-4f * (scale + wd.y);
-	const bool behind = wd.y == 0.f || czmin - wd.y >= g.miu + eps;    // only invalid depth / behind the band
-	const bool infront = inside && wd.x > 0.f && wd.x - czmax > g.miu + eps;
-	return !front ? 2 : outside ? 0 : !fits ? 2 : behind ? 0 : infront ? 1 : 2;
-}
-
-// append `n` staged entries (shared memory) to a global list: one atomic per flush
-template <typename T>
-__device__ __forceinline__ void flush_stage(T *__restrict__ list, unsigned *__restrict__ counter, const T *stage, int n, int lane) {
-	unsigned base = 0;
-	if (lane == 0) base = atomicAdd(counter, (unsigned)n);
-	base = __shfl_sync(0xffffffffu, base, 0);
-	for (int i = lane; i < n; i += 32) list[base + i] = stage[i];
-	__syncwarp();
-}
 
 // ---------------------------------------------------------------------------------------------
-// K1a: classification of the frame against the volume geometry -- everything K1b needs to know that does not
-// depend on the volume's contents, so it runs one frame ahead on a second stream.
-//   classify_kernel
-//     pass 1, one THREAD per super-block (box of 32 bricks): conservative CULL / FREE test of the box;
-//     pass 2, one WARP per surviving box, one brick per lane: CULL / FREE / MIXED.  FREE bricks become brick
-//     entries with a full mask, MIXED bricks go to the `mixed` id list.
-//   quad_kernel
-//     pass 3, one warp pass per MIXED brick, one quad per lane: SKIP / FREE / EXACT (classify_quad).  FREE quads
-//     become the brick's entry {id, mask}; EXACT quads go to the `exact` list.
-// The tile grids are staged into shared memory once per block by a TMA bulk copy.
+// K1a: classification.  One warp per super-block (static stride over a persistent grid): the whole
+// warp classifies the box, then -- unless the box is CULL or FREE as a whole -- each lane classifies
+// one brick.  Surviving bricks are appended to the MIXED / FREE lists with one atomic per warp and
+// list.  The tile grids are staged into shared memory once per block by a TMA bulk copy.
 // ---------------------------------------------------------------------------------------------
 template <bool VEC4, bool CULL, bool TMA_TILES>
 __global__ void __launch_bounds__(kK1aThreads) classify_kernel(VolGeom g, FrameView f, WorkLists wl)
@@ -574,127 +503,16 @@ __global__ void __launch_bounds__(kK1aThreads) classify_kernel(VolGeom g, FrameV
 		else if (cls == kFree) s_free[bf + __popc(fm & below)] = id;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0 && s_cnt[0]) s_base[0] = atomicAdd(wl.counts + 2, s_cnt[0]);
-	if (threadIdx.x == 1 && s_cnt[1]) s_base[1] = atomicAdd(wl.counts + 0, s_cnt[1]);
+	if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(wl.counts + threadIdx.x, s_cnt[threadIdx.x]);
 	__syncthreads();
 	for (unsigned i = threadIdx.x; i < s_cnt[0]; i += blockDim.x) wl.mixed[s_base[0] + i] = s_mixed[i];
-	// FREE bricks: one entry each, all quads (K1b masks the lanes beyond the volume's faces)
-	for (unsigned i = threadIdx.x; i < s_cnt[1]; i += blockDim.x) wl.bricks[s_base[1] + i] = make_uint2(s_free[i], 0xffffffffu);
-}
-
-// K1a pass 3 (see above).  Warps walk the MIXED id list with a static stride, two bricks per step so that the two
-// window look-ups are in flight together.  QUADS = false (scalar path, generic K, SFM_FLAG_NO_QUADS): every quad of a
-// MIXED brick is EXACT.
-template <bool VEC4, bool QUADS>
-__global__ void __launch_bounds__(kK1aThreads) quad_kernel(VolGeom g, FrameView f, WorkLists wl)
-{
-	constexpr int VEC = VEC4 ? 4 : 1;
-	const int zsh = VEC4 ? g.zl_log2 : 5;
-	const int CPW = 32 >> zsh;
-	const int csh = zsh + (VEC4 ? 2 : 0);
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int zq = lane & ((1 << zsh) - 1), ci = lane >> zsh;
-	extern __shared__ __align__(128) unsigned char smem_dyn[];
-	uint2 *s_bk = reinterpret_cast<uint2 *>(smem_dyn) + (size_t)warp * (kStageB + kStageX);
-	uint2 *s_xq = s_bk + kStageB;
-	int nbk = 0, nxq = 0;  // warp-uniform
-	const unsigned nm = wl.counts[2];
-	const unsigned below = (1u << lane) - 1u;
-	// dynamic distribution (kQuadGrab bricks per atomic): this kernel runs next to a resident wave of K1b, so only some of
-	// its blocks are on the machine at any time and a static split would leave work to blocks that start late
-	constexpr unsigned kQuadGrab = 16;
-	for (;;) {
-	unsigned i0 = 0;
-	if (lane == 0) i0 = atomicAdd(wl.counts + 3, kQuadGrab);
-	i0 = __shfl_sync(0xffffffffu, i0, 0);
-	if (i0 >= nm) break;
-	for (unsigned i = i0; i < min(i0 + kQuadGrab, nm); i += 2u) {
-		unsigned id[2];
-		int qx[2], y[2], zl[2], qc[2];
-#pragma unroll
-		for (int j = 0; j < 2; j++) {
-			id[j] = (i + j < nm) ? wl.mixed[i + j] : 0xffffffffu;
-			qx[j] = (int)(id[j] >> kIdXShift);
-			y[j] = (int)((id[j] >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW + ci;
-			zl[j] = (int)((id[j] & ((1u << kIdGShift) - 1u)) << csh) + zq * VEC;
-		}
-#pragma unroll
-		for (int j = 0; j < 2; j++) {
-			const bool in = id[j] != 0xffffffffu && y[j] < g.Dy && zl[j] < g.nz;
-			const int c = QUADS ? classify_quad<VEC>(f, g, in ? qx[j] : 0, in ? y[j] : 0, in ? zl[j] : 0) : 2;
-			qc[j] = in ? c : 0;
-		}
-#pragma unroll
-		for (int j = 0; j < 2; j++) {
-			const unsigned qf = __ballot_sync(0xffffffffu, qc[j] == 1), qe = __ballot_sync(0xffffffffu, qc[j] == 2);
-			if (qe) {
-				if (nxq + 32 > kStageX) { flush_stage(wl.exact, wl.counts + 1, s_xq, nxq, lane); nxq = 0; }
-				if (qc[j] == 2) s_xq[nxq + __popc(qe & below)] = make_uint2((unsigned)qx[j] | ((unsigned)y[j] << 16), (unsigned)zl[j]);
-				nxq += __popc(qe);
-			}
-			if (qf) {
-				if (nbk + 1 > kStageB) { flush_stage(wl.bricks, wl.counts + 0, s_bk, nbk, lane); nbk = 0; }
-				if (lane == 0) s_bk[nbk] = make_uint2(id[j], qf);
-				nbk++;
-			}
-			__syncwarp();
-		}
-	}
-	}
-	if (nbk) flush_stage(wl.bricks, wl.counts + 0, s_bk, nbk, lane);
-	if (nxq) flush_stage(wl.exact, wl.counts + 1, s_xq, nxq, lane);
+	for (unsigned i = threadIdx.x; i < s_cnt[1]; i += blockDim.x) wl.free_[s_base[1] + i] = s_free[i];
 }
 
 // ---------------------------------------------------------------------------------------------
-// K0b: per-pixel windowed depth range for K1b's quad classification.  win[y*W + x] = {min, max} of
-// depth/depth_scale (the same IEEE divide as K0, tsdf.cu:49) over the kWin x kWin pixel window anchored at
-// (x, y); pixels beyond the image are ignored, and the minimum counts invalid pixels as 0, so min > 0 <=> the
-// window has no hole.  The division is monotone, so min / max are taken on the raw u16 values.
-// ---------------------------------------------------------------------------------------------
-constexpr int kWinTX = 64, kWinTY = 16;  // output pixels per block
-
-__global__ void __launch_bounds__(256) window_kernel(const uint16_t *__restrict__ depth, int W, int H, float depth_scale,
-	float2 *__restrict__ win)
-{
-	constexpr int IW = kWinTX + kWin - 1, IH = kWinTY + kWin - 1;
-	__shared__ uint16_t s_lo[IH][IW + 1], s_hi[IH][IW + 1];  // inputs of the min / the max (outside the image: neutral)
-	__shared__ uint16_t s_rlo[IH][kWinTX], s_rhi[IH][kWinTX];  // after the row pass
-	const int x0 = blockIdx.x * kWinTX, y0 = blockIdx.y * kWinTY;
-	for (int i = threadIdx.x; i < IW * IH; i += blockDim.x) {
-		const int r = i / IW, c = i - r * IW, x = x0 + c, y = y0 + r;
-		const bool in = x < W && y < H;
-		const uint16_t d = in ? depth[(size_t)y * W + x] : (uint16_t)0;
-		s_lo[r][c] = in ? d : (uint16_t)0xffffu;
-		s_hi[r][c] = d;
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < kWinTX * IH; i += blockDim.x) {
-		const int r = i / kWinTX, c = i - r * kWinTX;
-		unsigned lo = 0xffffu, hi = 0;
-#pragma unroll
-		for (int k = 0; k < kWin; k++) { lo = min(lo, (unsigned)s_lo[r][c + k]); hi = max(hi, (unsigned)s_hi[r][c + k]); }
-		s_rlo[r][c] = (uint16_t)lo;
-		s_rhi[r][c] = (uint16_t)hi;
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < kWinTX * kWinTY; i += blockDim.x) {
-		const int r = i / kWinTX, c = i - r * kWinTX, x = x0 + c, y = y0 + r;
-		if (x >= W || y >= H) continue;
-		unsigned lo = 0xffffu, hi = 0;
-#pragma unroll
-		for (int k = 0; k < kWin; k++) { lo = min(lo, (unsigned)s_rlo[r + k][c]); hi = max(hi, (unsigned)s_rhi[r + k][c]); }
-		win[(size_t)y * W + x] = make_float2(__fdiv_rn((float)lo, depth_scale), __fdiv_rn((float)hi, depth_scale));
-	}
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1b: update.  Persistent warps alternate between the two lists K1a wrote:
-//   * EXACT quads, 32 per warp pass, one quad per lane, all lanes busy: per-voxel evaluation with the reference's
-//     exact op order (eval_quad), near-surface voxels deferred to the surface queue;
-//   * brick entries, kFetch per step: the lanes whose quad is FREE add 1 to four weights (and update the SDF when it
-//     is not already exactly 1.0f).  Only the lanes of the mask load anything, so SKIP quads cost no traffic.
-// Alternating the two keeps the warps that chase histogram sectors and the warps that stream weights mixed on every
-// SM (round 1 measured 0.199 -> 0.143 ms from that mixing alone).
+// K1b: update.  Persistent warps pull kFetch bricks at a time from the lists (MIXED first, the
+// cheap FREE bricks last, so the tail of the kernel is made of small items) -- every warp gets the
+// same amount of work to within a few bricks, whatever the geometry of the frame.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool LABELS, bool KCANON>
 __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
@@ -710,53 +528,123 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 	using I = typename VecT<VEC>::I;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int zq = lane & ((1 << zsh) - 1), ci = lane >> zsh;
-	const size_t lane_off = (size_t)ci * (size_t)g.nz + (size_t)(zq * VEC);  // lane's quad relative to the brick's first voxel
 	unsigned nU = 0, nS = 0;
 	// dynamic shared memory: per warp, kQueue deferred near-surface voxels {column, local z, pixel, weight}
 	extern __shared__ __align__(128) unsigned char smem_dyn[];
 	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
 	int qcount = 0;  // warp-uniform
-	const unsigned nbricks = wl.counts[0], nexact = wl.counts[1];
-	const unsigned npass = (nexact + 31u) >> 5;
-	const unsigned long long stream = l2_policy_stream();  // SDF / weight lines pass through L2 once per frame
-
-	// diff == 1.0f for the lane's VEC voxels (FREE quad): weight += 1, sdf = (sdf*w + 1)/(w + 1), which leaves an
-	// SDF of exactly 1.0f unchanged (steady state of free space: only the weight is written)
-	auto update_free = [&](size_t v0, const F &sv, I wv) {
+	const unsigned nmixed = wl.counts[0], total = nmixed + wl.counts[1];
+	auto brick_coords = [&](unsigned id, int &x, int &y, int &zl) {  // warp-uniform id + lane offsets
+		x = (int)(id >> kIdXShift);
+		y = (int)((id >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW + ci;
+		zl = (int)((id & ((1u << kIdGShift) - 1u)) << csh) + zq * VEC;
+	};
+	auto brick_voxel = [&](int x, int y, int zl, bool ok) { return ((size_t)x * g.Dy + (ok ? y : 0)) * (size_t)g.nz + (ok ? zl : 0); };
+	// Software pipeline: the SDF / weight quads of brick i+1 are requested before brick i is
+	// evaluated, so every warp keeps two bricks' worth of 128-bit loads in flight; the atomic that
+	// fetches the next group is in flight while this group is evaluated.
+	F sv_n{}; I wv_n{};
+	auto issue = [&](unsigned id) {
+		int x, y, zl;
+		brick_coords(id, x, y, zl);
+		if ((y < g.Dy) && (zl < g.nz)) {
+			const size_t v = brick_voxel(x, y, zl, true);
+			sv_n = *reinterpret_cast<const F *>(p.sdf + v);
+			wv_n = *reinterpret_cast<const I *>(p.wt + v);
+		}
+	};
+	// list position -> brick id.  SFM_K1_PERMUTE: positions walk each list with a stride coprime to its
+	// length, so bricks that sit next to each other in space (K1a appends 32 neighbours at a time) are
+	// evaluated far apart in time: warps that chase histogram sectors and warps that do arithmetic mix
+	// on every SM instead of the whole machine hitting the same kind of brick at once.
+	const unsigned nfree = total - nmixed;
+#if SFM_K1_PERMUTE
+	const unsigned pm = (nmixed % 4093u) ? 4093u : 4091u, pf = (nfree % 4093u) ? 4093u : 4091u;
+#endif
+	auto list_at = [&](unsigned i) {
+#if SFM_K1_PERMUTE
+		if (i < nmixed) return wl.mixed[nmixed < (1u << 20) ? (i * pm) % nmixed : i];
+		const unsigned k = i - nmixed;
+		return wl.free_[nfree < (1u << 20) ? (k * pf) % nfree : k];
+#else
+		return i < nmixed ? wl.mixed[i] : wl.free_[i - nmixed];
+#endif
+	};
+	auto fetch = [&]() {  // lane 0 holds the result; broadcast when it is needed
+		unsigned b = 0;
+		if (lane == 0) b = atomicAdd(wl.counts + 2, (unsigned)kFetch);
+		return b;
+	};
+	// prefetch.global.L2 of the SDF / weight lines of bricks 1.. of a freshly fetched group (brick 0 is
+	// requested into registers right away): by the time the 128-bit loads ask for them they sit in L2
+	auto prefetch_group = [&](unsigned ids, int cnt) {
+		// the lanes that start a column segment (zq == 0) request its SDF and weight lines
+#pragma unroll
+		for (int bi = 1; bi < kFetch; bi++) {
+			const unsigned id = __shfl_sync(0xffffffffu, ids, bi);
+			if (bi < cnt && zq == 0 && !(f.debug & 32)) {
+				int x, y, zl;
+				brick_coords(id, x, y, zl);
+				if (y < g.Dy) {
+					const size_t v = ((size_t)x * g.Dy + y) * (size_t)g.nz + zl;
+					prefetch_l2(p.sdf + v);
+					prefetch_l2(p.wt + v);
+				}
+			}
+		}
+	};
+	unsigned base = __shfl_sync(0xffffffffu, fetch(), 0);
+	int n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
+	unsigned my_id = lane < n ? list_at(base + lane) : 0u;
+	unsigned next_raw = fetch();
+	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+	if (n > 1) prefetch_group(my_id, n);
+	while (n > 0) {
+	for (int i = 0; i < n; i++) {
+		const unsigned id = __shfl_sync(0xffffffffu, my_id, i);
+		const bool is_free = base + i >= nmixed;  // warp-uniform
+		const F sv = sv_n;
+		I wv = wv_n;
+		int x, y, zl;
+		brick_coords(id, x, y, zl);
+		const bool ok = (y < g.Dy) && (zl < g.nz);
+		const size_t v0 = brick_voxel(x, y, zl, ok);
+		// prefetch the next brick
+		if (i + 1 < n) issue(__shfl_sync(0xffffffffu, my_id, i + 1));
+		if (f.debug & 1) continue;  // ablation: fetches and loads only
 		F sn = sv;
 		float *sp = reinterpret_cast<float *>(&sn);
 		int *w = reinterpret_cast<int *>(&wv);
-		bool steady = true;
+		if (is_free) {
+			// FREE brick: every voxel gets diff == 1.0f (> near_gate, so no colour / histogram update)
+			if (ok) {
+				bool steady = true;
 #pragma unroll
-		for (int k = 0; k < VEC; k++) steady &= (sp[k] == 1.0f) & ((unsigned)w[k] < (1u << 24));
+				for (int k = 0; k < VEC; k++) steady &= (sp[k] == 1.0f) & ((unsigned)w[k] < (1u << 24));
 #pragma unroll
-		for (int k = 0; k < VEC; k++) {
-			if (!steady) sp[k] = sdf_update(sp[k], w[k], 1.0f);
-			w[k] += 1;
+				for (int k = 0; k < VEC; k++) {
+					if (!steady) sp[k] = sdf_update(sp[k], w[k], 1.0f);
+					w[k] += 1;
+				}
+				nU += VEC;
+				*reinterpret_cast<I *>(p.wt + v0) = wv;
+				if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
+			}
+			continue;
 		}
-		nU += VEC;
-		st_hint(reinterpret_cast<I *>(p.wt + v0), wv, stream);
-		if (!steady && !same_bits(sv, sn)) st_hint(reinterpret_cast<F *>(p.sdf + v0), sn, stream);
-	};
-
-	// Per-voxel evaluation of the lane's VEC voxels (x, y, zl .. zl+VEC-1), tsdf.cu:30-68, phased so that the
-	// independent loads of the lane's voxels are in flight together instead of one dependent miss after
-	// another.  Called by all 32 lanes (the surface queue uses warp ballots); lanes with !ok do nothing.
-	// The quad comes packed as in the exact list ({x | y << 16, zl}); coordinates and the voxel index are unpacked
-	// where they are used instead of being kept in registers across the whole evaluation.
-	auto eval_quad = [&](const uint2 e, bool ok, F sn, I wv) {
-		float *sp = reinterpret_cast<float *>(&sn);
-		int *w = reinterpret_cast<int *>(&wv);
-		const int zl = (int)e.y;
-		const float px = __fmaf_rn((float)(e.x & 0xffffu), g.vx, g.sx);
-		const float py = __fmaf_rn((float)(e.x >> 16), g.vy, g.sy);
+		if (f.debug & 4) continue;  // ablation: FREE bricks only
+		// MIXED brick: per-voxel evaluation (tsdf.cu:30-68), phased so that the independent loads of
+		// the lane's VEC voxels are in flight together instead of one dependent miss after another.
+		// All 32 lanes stay converged through this block (the surface queue below uses warp ballots).
+		const float px = __fmaf_rn((float)x, g.vx, g.sx);
+		const float py = __fmaf_rn((float)y, g.vy, g.sy);
 		const float h0 = affine_hoist(px, py, f.E[0], f.E[1]);
 		const float h1 = affine_hoist(px, py, f.E[4], f.E[5]);
 		const float h2 = affine_hoist(px, py, f.E[8], f.E[9]);
 		// The common case of every step is straight-line code; the rare exact re-evaluations are
 		// collected in bit masks and handled after the loop by out-of-line helpers, so the hot path
 		// carries no per-voxel branches.
-		float czv[VEC], diffv[VEC];
+		float czv[VEC], diffv[VEC], sxv[VEC], syv[VEC], szv[VEC];
 		int img[VEC];
 		unsigned inb = 0, inexact = 0;
 		// phase 1: projection -> pixel (no memory).  tsdf.cu:30-46
@@ -768,6 +656,7 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 			czv[k] = affine_finish(h2, pz, f.E[10], f.E[11]);
 			float sx, sy, sz;
 			cam_to_screen<KCANON>(f, cx, cy, czv[k], sx, sy, sz);
+			sxv[k] = sx; syv[k] = sy; szv[k] = sz;
 			// ix = floor(RN(sx/sz)) without the IEEE divide: see pixel_floor_is_safe()
 			float r;
 			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sz));  // .ftz: one MUFU.RCP, no denormal rescaling
@@ -781,11 +670,7 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 #pragma unroll
 			for (int k = 0; k < VEC; k++)
 				if ((inexact >> k) & 1u) {
-					// (recomputed rather than kept: three registers per voxel across the whole phase otherwise)
-					const float pz = __fmaf_rn((float)(g.z0 + zl + k), g.vz, g.sz);
-					float sx, sy, sz;
-					cam_to_screen<KCANON>(f, affine_finish(h0, pz, f.E[2], f.E[3]), affine_finish(h1, pz, f.E[6], f.E[7]), czv[k], sx, sy, sz);
-					const int ix = __float2int_rd(exact_div(sx, sz)), iy = __float2int_rd(exact_div(sy, sz));
+					const int ix = __float2int_rd(exact_div(sxv[k], szv[k])), iy = __float2int_rd(exact_div(syv[k], szv[k]));
 					const bool in = (unsigned)ix < (unsigned)f.W && (unsigned)iy < (unsigned)f.H;
 					inb = (inb & ~(1u << k)) | ((in ? 1u : 0u) << k);
 					img[k] = iy * f.W + ix;
@@ -821,16 +706,14 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		// a per-warp queue and processed 32 at a time by all lanes (drain_surface_queue), instead of a
 		// few lanes chasing label -> histogram loads one voxel after another
 		if ((f.debug & 2)) surface = 0;      // ablation: no near-surface updates
-		// The queue is drained one evaluation LATE: the entries it holds were queued -- and their colour and
-		// histogram sectors requested with prefetch.global.L2 -- during an earlier evaluation, so
+		// The queue is drained one brick LATE: the entries it holds were queued -- and their colour and
+		// histogram sectors requested with prefetch.global.L2 -- while an earlier brick was evaluated, so
 		// the drain's dependent loads hit L2 instead of waiting for DRAM one after another.
-		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another 32 x VEC voxels: drain
+		if (qcount >= kQueue - 32 * VEC) {  // not enough room for another brick: drain
 			nS += drain_surface_queue<LABELS>(p, g, f, q, qcount, lane, err);
 			qcount = 0;
 		}
 		if (__any_sync(0xffffffffu, surface != 0)) {
-			const int x = (int)(e.x & 0xffffu), y = (int)(e.x >> 16);
-			const size_t v0 = ((size_t)x * g.Dy + y) * (size_t)g.nz + zl;
 			if (surface) {
 				// surface-block map (Planes::occ): idempotent byte stores, no atomics.  A lane's VEC voxels
 				// share (x, y) and lie in one 8-block along z when VEC == 4; the low-face neighbours are
@@ -862,15 +745,17 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 				const unsigned m = __ballot_sync(0xffffffffu, sf);
 				if (sf) {
 					const int slot = qcount + __popc(m & ((1u << lane) - 1u));
-					q[slot] = make_uint4((unsigned)x * (unsigned)g.Dy + (unsigned)y, (unsigned)(zl + k), (unsigned)img[k], (unsigned)w[k]);
+					const unsigned col = (unsigned)x * (unsigned)g.Dy + (unsigned)y;
+					q[slot] = make_uint4(col, (unsigned)(zl + k), (unsigned)img[k], (unsigned)w[k]);
 					if (!(f.debug & 16)) {
-						// colour and histogram sectors are requested now and touched by the drain one evaluation later: the
-						// drain's loads hit L2, and its reductions find their sector resident (a RED into a sector that is
-						// still in DRAM occupies the L2's atomic unit until the fill arrives and backs up into the SMs)
+						// colour and histogram sectors are requested now and touched by the drain one brick later: the
+						// drain's loads hit L2, and its reductions find their sector resident (a RED into a sector that
+						// is still in DRAM occupies the L2's atomic unit until the fill arrives and backs up into the
+						// SMs: measured 0.194 ms without this prefetch, 0.131 ms with it)
 						prefetch_l2_keep(p.color + (v0 + k) * 3);
 						if (LABELS) {
 							const unsigned label = __ldg(f.mask + img[k]);
-							if ((int)label < p.bins) prefetch_l2_keep(p.hist + hist_index((size_t)x * g.Dy + y, zl + k, g.ngz, p.bins, (int)label));
+							if ((int)label < p.bins) prefetch_l2_keep(p.hist + hist_index(col, zl + k, g.ngz, p.bins, (int)label));
 						}
 					}
 				}
@@ -879,115 +764,28 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		}
 		if (touched) {
 			// steady state of free space: sdf == 1.0f, diff == 1.0f, (1*w + 1)/(w+1) == 1.0f exactly -> only w changes
-			bool changed = false;
+			bool steady = true;
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				if ((touched >> k) & 1u) steady &= (sp[k] == 1.0f) & (nd[k] == 1.0f) & ((unsigned)w[k] < (1u << 24));
 #pragma unroll
 			for (int k = 0; k < VEC; k++)
 				if ((touched >> k) & 1u) {
-					const float s_new = sdf_update(sp[k], w[k], nd[k]);  // tsdf.cu:56 (exactly 1.0f stays without a divide)
-					changed |= __float_as_uint(s_new) != __float_as_uint(sp[k]);
-					sp[k] = s_new;
-					w[k] += 1;                                           // tsdf.cu:68
+					if (!steady) sp[k] = sdf_update(sp[k], w[k], nd[k]);  // tsdf.cu:56
+					w[k] += 1;                                             // tsdf.cu:68
 				}
 			nU += __popc(touched);
-			const size_t v0 = ((size_t)(e.x & 0xffffu) * g.Dy + (e.x >> 16)) * (size_t)g.nz + zl;
-			st_hint(reinterpret_cast<I *>(p.wt + v0), wv, stream);
-			if (changed) st_hint(reinterpret_cast<F *>(p.sdf + v0), sn, stream);  // an SDF quad whose bits did not change is not written back
+			*reinterpret_cast<I *>(p.wt + v0) = wv;
+			if (!steady && !same_bits(sv, sn)) *reinterpret_cast<F *>(p.sdf + v0) = sn;
 		}
-	};
-
-	// Work distribution: a static stride over the grid's warps, no cursor atomics.  A warp's items are known up front,
-	// so nothing on its path is a chain of dependent misses: the list entries of item i+1 are loaded while item i is
-	// processed, the voxel lines they point to are requested with prefetch.global.L2 one item ahead, and the exact
-	// quad's own 128-bit loads are issued before the brick group of the same step and consumed after it.  (The first
-	// version of this kernel fetched every item with an atomic and then chased entry -> voxel loads: 22 items per warp
-	// x 3 dependent round trips made the streaming skeleton alone cost 0.096 ms.)
-	const unsigned nwarps = gridDim.x * (kK1Threads / 32), wid = blockIdx.x * (kK1Threads / 32) + warp;
-	const unsigned ngroups = (nbricks + kFetch - 1) / kFetch;
-	const unsigned kNone = 0xffffffffu;  // x = y = 65535 never occurs (dims <= 65535)
-	auto load_exact = [&](unsigned ps) {
-		const unsigned idx = ps * 32u + (unsigned)lane;
-		return (ps < npass && idx < nexact) ? wl.exact[idx] : make_uint2(kNone, 0u);
-	};
-	auto load_bricks = [&](unsigned gp) {
-		const unsigned i = gp * kFetch + (unsigned)lane;
-		return (lane < kFetch && gp < ngroups && i < nbricks) ? wl.bricks[i] : make_uint2(0u, 0u);  // empty mask: nothing to do
-	};
-	auto quad_voxel = [&](const uint2 e) { return ((size_t)(e.x & 0xffffu) * g.Dy + (e.x >> 16)) * (size_t)g.nz + e.y; };
-	auto brick_voxel = [&](unsigned id) {  // first voxel of the lane's quad
-		const int bx = (int)(id >> kIdXShift);
-		const int by = (int)((id >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW;
-		const int bz = (int)((id & ((1u << kIdGShift) - 1u)) << csh);
-		return ((size_t)bx * g.Dy + by) * (size_t)g.nz + bz + lane_off;
-	};
-	auto brick_lane_inside = [&](unsigned id) {
-		const int by = (int)((id >> kIdGShift) & ((1u << (kIdXShift - kIdGShift)) - 1u)) * CPW;
-		const int bz = (int)((id & ((1u << kIdGShift) - 1u)) << csh);
-		return (by + ci < g.Dy) && (bz + zq * VEC < g.nz);
-	};
-	const unsigned colmask = (zsh == 5 ? 0xffffffffu : ((1u << (1 << zsh)) - 1u)) << (ci << zsh);  // the lanes of this lane's column
-	auto prefetch_items = [&](const uint2 e, const uint2 b) {
-		if (f.debug & 32) return;
-		if (e.x != kNone) {
-			const size_t v = quad_voxel(e);
-			prefetch_l2(p.sdf + v);
-			prefetch_l2(p.wt + v);
-		}
-#pragma unroll
-		for (int i = 0; i < kFetch; i++) {
-			const unsigned id = __shfl_sync(0xffffffffu, b.x, i), fm = __shfl_sync(0xffffffffu, b.y, i);
-			if (zq == 0 && (fm & colmask) && brick_lane_inside(id)) {  // the lane that starts a column requests its lines
-				const size_t v = brick_voxel(id);
-				prefetch_l2(p.sdf + v);
-				prefetch_l2(p.wt + v);
-			}
-		}
-	};
-	unsigned pass = wid, grp = wid;
-	uint2 e_cur = load_exact(pass), b_cur = load_bricks(grp);
-	while (pass < npass || grp < ngroups) {  // warp-uniform
-		// 1. the exact quad's loads
-		const bool ok = e_cur.x != kNone;
-		F sv{}; I wv{};
-		if (ok) {
-			const size_t v0 = quad_voxel(e_cur);
-			sv = ld_hint(reinterpret_cast<const F *>(p.sdf + v0), stream);
-			wv = ld_hint(reinterpret_cast<const I *>(p.wt + v0), stream);
-		}
-		// 2. the next step's list entries
-		const uint2 e_next = load_exact(pass + nwarps), b_next = load_bricks(grp + nwarps);
-		// 3. the brick group: FREE quads, two bricks at a time (their loads are issued before the first is used)
-		if (grp < ngroups) {
-#pragma unroll
-			for (int i0 = 0; i0 < kFetch; i0 += 2) {
-				F bs[2]; I bw[2];
-				size_t v0[2];
-				bool mine[2];
-#pragma unroll
-				for (int j = 0; j < 2; j++) {
-					const unsigned id = __shfl_sync(0xffffffffu, b_cur.x, i0 + j), fm = __shfl_sync(0xffffffffu, b_cur.y, i0 + j);
-					mine[j] = ((fm >> lane) & 1u) && brick_lane_inside(id);
-					v0[j] = brick_voxel(id);
-					if (mine[j]) {
-						bs[j] = ld_hint(reinterpret_cast<const F *>(p.sdf + v0[j]), stream);
-						bw[j] = ld_hint(reinterpret_cast<const I *>(p.wt + v0[j]), stream);
-					}
-				}
-				if (!(f.debug & 1)) {
-#pragma unroll
-					for (int j = 0; j < 2; j++)
-						if (mine[j]) update_free(v0[j], bs[j], bw[j]);
-				}
-			}
-		}
-		// 4. the exact pass
-		if (pass < npass && !(f.debug & 5)) eval_quad(ok ? e_cur : make_uint2(0u, 0u), ok, sv, wv);
-		// 5. request the next step's voxel lines
-		prefetch_items(e_next, b_next);
-		e_cur = e_next;
-		b_cur = b_next;
-		pass += nwarps;
-		grp += nwarps;
 	}
+	base = __shfl_sync(0xffffffffu, next_raw, 0);
+	n = base < total ? (int)min((unsigned)kFetch, total - base) : 0;
+	my_id = lane < n ? list_at(base + lane) : 0u;
+	next_raw = fetch();
+	if (n) issue(__shfl_sync(0xffffffffu, my_id, 0));
+	if (n > 1) prefetch_group(my_id, n);
+	}  // fetch loop
 	if (qcount) nS += drain_surface_queue<LABELS>(p, g, f, q, qcount, lane, err);
 
 	// fold U / S: warp shuffle, then one spread atomic pair per warp (no block barrier: warps with

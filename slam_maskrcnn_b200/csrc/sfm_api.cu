@@ -115,10 +115,8 @@ struct sfm_volume {
 	struct PrepCtx {
 		uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
 		float *d_depth_m = nullptr;
-		float2 *d_win = nullptr;                     // windowed depth range per pixel (K0b -> K1b quad classification)
 		unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
-		uint32_t *d_list_mixed = nullptr;                          // K1a pass 2 -> pass 3: MIXED brick ids (one slot per brick)
-		uint2 *d_list_bricks = nullptr, *d_list_exact = nullptr;   // K1a -> K1b: brick entries (one slot per brick), EXACT quads (one per quad)
+		uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
 		cudaEvent_t ev_ready = nullptr;  // K1a of the frame that uses this context is done (prep_stream)
 		cudaEvent_t ev_free = nullptr;   // K1b of that frame is done (main stream): the context may be rewritten
 	} ctx[3];
@@ -170,7 +168,6 @@ struct sfm_volume {
 	static constexpr int kRing = 2048;  // per-call event pairs around K1 (integrate kernel only)
 	cudaEvent_t ev_k0[kRing] = {}, ev_km[kRing] = {};  // around K1a (prep_stream)
 	cudaEvent_t ev_kb[kRing] = {}, ev_k1[kRing] = {};  // around K1b (main stream)
-	cudaEvent_t ev_kq[kRing] = {};                      // before K1a pass 3 (main stream; it ends where K1b begins)
 	uint64_t n_integrate = 0;
 	uint64_t launches = 0;
 	uint64_t stat_U_seen = 0, stat_S_seen = 0;  // cumulative totals already reported by sfm_frame_stats
@@ -183,7 +180,6 @@ struct sfm_volume {
 	uint32_t *d_hist_chunk = nullptr; // staging for sfm_download / sfm_upload (kHistChunk bytes)
 	unsigned *d_hist_max = nullptr;
 	uint32_t hist_bound = 0;     // upper bound of every bin: frames integrated (+ the largest uploaded value)
-	int k1q_blocks_per_sm = 16; // grid of quad_kernel (K1a pass 3), blocks per SM
 	int debug_ablate = 0;      // SFM_DEBUG_ABLATE, read once at creation and only under SFM_FLAG_DEBUG_ABLATE
 };
 
@@ -296,7 +292,6 @@ FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, con
 	f.tilemin = c.d_tilemin;
 	f.tile_bytes = (unsigned)v->tile_bytes;
 	f.depth_m = c.d_depth_m;
-	f.win = c.d_win;
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
 	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
@@ -314,11 +309,7 @@ FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, con
 	f.cull_t = tt;
 	f.cull_k2 = k2;
 	f.cull_slack0 = 1.f + 1e-3f * std::max(k0, k1) / std::max(k2, 1e-20f);
-	f.cull_scale = lin * (std::max(fabsf(v->g.sx), fabsf(v->g.ex)) + std::max(fabsf(v->g.sy), fabsf(v->g.ey)) +
-		std::max(fabsf(v->g.sz), fabsf(v->g.ez)) + 1.f) + tt;
-	f.cull_kx = k0;
-	f.cull_ky = k1;
-	f.debug = v->debug_ablate | ((v->desc.flags & SFM_FLAG_NO_QUADS) ? 64 : 0);
+	f.debug = v->debug_ablate;
 	return f;
 }
 
@@ -331,7 +322,7 @@ bool canonical_k(const sfm_volume *v, const FrameView &f) {
 	return canon;
 }
 
-// K1a: classification into the work lists (classify_kernel: boxes and bricks; quad_kernel: the quads of MIXED bricks)
+// K1a: brick classification into the work lists
 template <bool VEC4, bool CULL, bool TMA_TILES>
 void launch_classify2(sfm_volume *v, const FrameView &f, const WorkLists &wl, long long nsb) {
 	// dynamic shared memory: [TMA-staged tile grids] [block-local MIXED list] [block-local FREE list]
@@ -360,17 +351,6 @@ void launch_classify(sfm_volume *v, const FrameView &f, const WorkLists &wl, lon
 	if (!cull) launch_classify2<VEC4, false, false>(v, f, wl, nsb);
 	else if (tma) launch_classify2<VEC4, true, true>(v, f, wl, nsb);
 	else launch_classify2<VEC4, true, false>(v, f, wl, nsb);
-}
-
-// pass 3: quads of the MIXED bricks.  The list length is only known on the device: a grid of resident warps walks it.
-template <bool VEC4>
-void launch_quads(sfm_volume *v, const FrameView &f, const WorkLists &wl) {
-	// quad classification (classify_quad) assumes the pinhole K and the 128-bit path
-	const bool quads = VEC4 && canonical_k(v, f) && !(v->desc.flags & SFM_FLAG_NO_QUADS);
-	const size_t smem = (size_t)(kK1aThreads / 32) * (kStageB + kStageX) * sizeof(uint2);
-	const int blocks = v->num_sms * v->k1q_blocks_per_sm;
-	if (quads) quad_kernel<VEC4, VEC4><<<blocks, kK1aThreads, smem, v->stream>>>(v->g, f, wl);
-	else quad_kernel<VEC4, false><<<blocks, kK1aThreads, smem, v->stream>>>(v->g, f, wl);
 }
 
 // K1b: update of the listed bricks
@@ -440,16 +420,13 @@ int enqueue_prepare(sfm_volume *v, const void *d_depth, const void *d_rgb, const
 	prep_frame_kernel<<<prep_blocks, 256, 0, v->prep_stream>>>(f.depth, v->bins > 0 ? f.mask : nullptr, v->W, v->H, v->TW, v->TH,
 		v->bins, v->desc.depth_scale, c.d_tilemax, c.d_tilemin, c.d_depth_m, v->d_err, c.d_work);
 	LAUNCH_CHECK(v);
-	window_kernel<<<dim3((v->W + kWinTX - 1) / kWinTX, (v->H + kWinTY - 1) / kWinTY), 256, 0, v->prep_stream>>>(f.depth, v->W, v->H,
-		v->desc.depth_scale, c.d_win);
-	LAUNCH_CHECK(v);
 	const bool vec4 = (v->g.nz % 4 == 0);
 	// K1a work items: super-blocks of kSbX x-planes x kSbG brick rows x one z chunk (k_integrate.cuh)
 	const int cpw = vec4 ? (32 >> v->g.zl_log2) : 1, chunk = vec4 ? (4 << v->g.zl_log2) : 32;
 	const long long rows = (v->g.Dy + cpw - 1) / cpw;
 	const long long nsb = (long long)((v->g.Dx + kSbX - 1) / kSbX) * ((rows + kSbG - 1) / kSbG) * ((v->g.nz + chunk - 1) / chunk);
 	if (nsb >= (1LL << 31)) return fail(SFM_ERR_INVALID, "volume too large for the 31-bit super-block ids");
-	const WorkLists wl{c.d_list_mixed, c.d_list_bricks, c.d_list_exact, c.d_work};
+	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
 	CU(cudaEventRecord(v->ev_k0[slot], v->prep_stream));
 	if (vec4) launch_classify<true>(v, f, wl, nsb);
 	else launch_classify<false>(v, f, wl, nsb);
@@ -466,17 +443,10 @@ int enqueue_update(sfm_volume *v, const void *d_depth, const void *d_rgb, const 
 	const FrameView f = make_frame_view(v, c, d_depth, d_rgb, d_mask, E16);
 	const int slot = (int)(v->n_integrate % sfm_volume::kRing);
 	const bool vec4 = (v->g.nz % 4 == 0);
-	const WorkLists wl{c.d_list_mixed, c.d_list_bricks, c.d_list_exact, c.d_work};
+	const WorkLists wl{c.d_list_mixed, c.d_list_free, c.d_work};
 	if (v->bins > 0 && v->hist_bound >= 65535u)
 		return fail(SFM_ERR_INVALID, "the histogram bins are 16 bits wide inside the library: at most 65535 labelled frames per volume");
 	CU(cudaStreamWaitEvent(v->stream, c.ev_ready, 0));
-	// K1a pass 3 (quads of the MIXED bricks) runs on the MAIN stream, between the previous frame's update and this
-	// one: it needs the whole machine for ~30 us; next to a resident wave of K1b (prep_stream, like passes 1 + 2) it got
-	// one block per SM and held the next update back for longer than that (measured: step 0.173 vs 0.16 ms)
-	CU(cudaEventRecord(v->ev_kq[slot], v->stream));
-	if (vec4) launch_quads<true>(v, f, wl);
-	else launch_quads<false>(v, f, wl);
-	LAUNCH_CHECK(v);
 	CU(cudaEventRecord(v->ev_kb[slot], v->stream));
 	if (vec4) {
 		if (v->bins > 0) launch_update<4, true>(v, f, wl, gate);
@@ -919,7 +889,6 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	v->desc = *desc;
 	if (desc->flags & SFM_FLAG_DEBUG_ABLATE) {  // profiling only: a stray environment variable alone changes nothing
 		if (const char *e = getenv("SFM_DEBUG_ABLATE")) v->debug_ablate = atoi(e) & ~64;
-		if (const char *e = getenv("SFM_K1Q_BLOCKS_PER_SM")) v->k1q_blocks_per_sm = std::max(1, std::min(16, atoi(e)));
 	}
 	v->bins = desc->bins;
 	v->W = desc->width;
@@ -961,7 +930,6 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k0[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_km[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_kb[i]));
-		CU_OR_DESTROY(cudaEventCreate(&v->ev_kq[i]));
 		CU_OR_DESTROY(cudaEventCreate(&v->ev_k1[i]));
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->planes.sdf, v->nvox * 4));
@@ -1008,7 +976,6 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		CU_OR_DESTROY(cudaMemset(c.d_tilemax, 0, v->tile_bytes));
 		c.d_tilemin = c.d_tilemax + (size_t)v->TW * v->TH;
 		CU_OR_DESTROY(cudaMalloc(&c.d_depth_m, npx * 4));
-		CU_OR_DESTROY(cudaMalloc(&c.d_win, npx * sizeof(float2)));
 		CU_OR_DESTROY(cudaMalloc(&c.d_work, 32));
 		CU_OR_DESTROY(cudaMemset(c.d_work, 0, 32));
 		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
@@ -1042,13 +1009,9 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 			return fail(SFM_ERR_INVALID, "volume too large for the packed brick ids (x <= 2048, y <= 8192 (2048 when nz % 4 != 0), nz <= 32768)");
 		}
 		v->nbricks = (size_t)v->g.Dx * rows * chunks;
-		// exact-quad list: one slot per quad of the volume (worst case: every quad of every brick is EXACT, which is
-		// what SFM_FLAG_NO_CULL + SFM_FLAG_NO_QUADS produce); 2 bytes per voxel on the 128-bit path
-		const size_t nquads = vec4 ? v->nvox / 4 : v->nbricks * 32;
 		for (auto &c : v->ctx) {
-			CU_OR_DESTROY(cudaMalloc(&c.d_list_mixed, v->nbricks * sizeof(uint32_t)));
-			CU_OR_DESTROY(cudaMalloc(&c.d_list_bricks, v->nbricks * sizeof(uint2)));
-			CU_OR_DESTROY(cudaMalloc(&c.d_list_exact, nquads * sizeof(uint2)));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_mixed, v->nbricks * 4));
+			CU_OR_DESTROY(cudaMalloc(&c.d_list_free, v->nbricks * 4));
 		}
 	}
 	v->num_sms = prop.multiProcessorCount;
@@ -1098,7 +1061,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
 	if (v->prep_stream) cudaStreamDestroy(v->prep_stream);
 	for (auto &c : v->ctx) {
-		cudaFree(c.d_tilemax); cudaFree(c.d_depth_m); cudaFree(c.d_win); cudaFree(c.d_work); cudaFree(c.d_list_mixed); cudaFree(c.d_list_bricks); cudaFree(c.d_list_exact);
+		cudaFree(c.d_tilemax); cudaFree(c.d_depth_m); cudaFree(c.d_work); cudaFree(c.d_list_mixed); cudaFree(c.d_list_free);
 		if (c.ev_ready) cudaEventDestroy(c.ev_ready);
 		if (c.ev_free) cudaEventDestroy(c.ev_free);
 	}
@@ -1123,7 +1086,6 @@ void sfm_destroy(sfm_volume *v) {
 		if (v->ev_k0[i]) cudaEventDestroy(v->ev_k0[i]);
 		if (v->ev_km[i]) cudaEventDestroy(v->ev_km[i]);
 		if (v->ev_kb[i]) cudaEventDestroy(v->ev_kb[i]);
-		if (v->ev_kq[i]) cudaEventDestroy(v->ev_kq[i]);
 		if (v->ev_k1[i]) cudaEventDestroy(v->ev_k1[i]);
 	}
 	if (v->own_stream && v->stream) cudaStreamDestroy(v->stream);
@@ -1730,9 +1692,9 @@ int sfm_integrate_times(sfm_volume *v, float *ms, int n) {
 	for (int i = 0; i < n; i++) {
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
-		float a = 0.f, b = 0.f;  // K1a passes 1 + 2 (prep_stream) + pass 3 and K1b (main stream)
+		float a = 0.f, b = 0.f;  // K1a (prep_stream) + K1b (main stream): the two may overlap other frames' kernels
 		CU(cudaEventElapsedTime(&a, v->ev_k0[slot], v->ev_km[slot]));
-		CU(cudaEventElapsedTime(&b, v->ev_kq[slot], v->ev_k1[slot]));
+		CU(cudaEventElapsedTime(&b, v->ev_kb[slot], v->ev_k1[slot]));
 		ms[i] = a + b;
 	}
 	return SFM_OK;
@@ -1746,10 +1708,7 @@ int sfm_integrate_times2(sfm_volume *v, float *ms_classify, float *ms_update, in
 	for (int i = 0; i < n; i++) {
 		const int slot = (int)((v->n_integrate - n + i) % sfm_volume::kRing);
 		CU(cudaEventSynchronize(v->ev_k1[slot]));
-		float a = 0.f, q = 0.f;
-		CU(cudaEventElapsedTime(&a, v->ev_k0[slot], v->ev_km[slot]));
-		CU(cudaEventElapsedTime(&q, v->ev_kq[slot], v->ev_kb[slot]));
-		ms_classify[i] = a + q;  // K1a passes 1 + 2 (prep stream, overlapped) + pass 3 (main stream)
+		CU(cudaEventElapsedTime(ms_classify + i, v->ev_k0[slot], v->ev_km[slot]));
 		CU(cudaEventElapsedTime(ms_update + i, v->ev_kb[slot], v->ev_k1[slot]));
 	}
 	return SFM_OK;

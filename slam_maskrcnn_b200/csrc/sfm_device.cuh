@@ -73,8 +73,6 @@ struct FrameView {
 	const uint16_t *tilemin;  // [TH][TW] min depth per tile, invalid (0) included: > 0 <=> no hole in the tile
 	unsigned tile_bytes;      // bytes of [tilemax | tilemin] (contiguous, multiple of 16) for the TMA bulk copy
 	const float *depth_m;     // [H][W] depth/depth_scale in f32 (IEEE divide), 0 = invalid
-	const float2 *win;        // [H][W] {min, max} of depth_m over the kWin x kWin window anchored at the pixel (K0b);
-	                          // the minimum counts invalid pixels as 0, pixels beyond the image are ignored
 	int W, H, TW, TH;
 	float E[12];  // rows 0..2 of extrinsic2init (row-major 3x4)
 	float K[9];   // rows 0..2, cols 0..2 of the intrinsic matrix
@@ -84,9 +82,7 @@ struct FrameView {
 	float cull_t;       // max_r |E[r][3]|
 	float cull_k2;      // |K20|+|K21|+|K22|
 	float cull_slack0;  // constant pixel slack
-	float cull_scale;   // cull_lin * (max over the volume of |px|+|py|+|pz|, + 1) + cull_t: bound of every camera coordinate
-	float cull_kx, cull_ky;  // |K00|+|K01|+|K02|, |K10|+|K11|+|K12|: pixel-coordinate sensitivity (quad classification)
-	int debug;          // ablation switches for profiling (0 in production; bit 64 = SFM_FLAG_NO_QUADS)
+	int debug;          // ablation switches for profiling (0 in production)
 };
 
 // dot(float4 row,(p,1)) as the reference compiles it (helper_math.h:1249-1252; tsdf.cu:31-33):

@@ -92,21 +92,6 @@ def test_cull_is_exact():
     assert sa == sb
 
 
-@pytest.mark.parametrize("dims,wh,yaw", [((96, 96, 96), (160, 120), 4.0), ((128, 128, 128), (640, 480), 2.0), ((72, 64, 200), (320, 240), 7.0)])
-def test_quad_classification_is_exact(dims, wh, yaw):
-    """K1b's quad-level SKIP / FREE / EXACT classification (windowed depth range, two end voxels per quad) vs every
-    quad through the exact per-voxel path (SFM_FLAG_NO_QUADS), and vs brick culling off on top of that."""
-    from slam_maskrcnn_b200 import FLAG_NO_QUADS, FLAG_NO_CULL
-    sc = Scenario(dims=dims, bins=16, width=wh[0], height=wh[1], frames=6, yaw_step_deg=yaw)
-    a, sa = run_ours(sc, flags=0)
-    b, sb = run_ours(sc, flags=FLAG_NO_QUADS)
-    c, sc_ = run_ours(sc, flags=FLAG_NO_CULL)
-    assert_planes_equal(a, b, "quad classes vs exact path")
-    assert_planes_equal(a, c, "quad classes on all bricks (no brick cull) vs default")
-    assert sa == sb == sc_
-    assert sum(u for u, _ in sa) > 0
-
-
 def test_labels_off_mode():
     """bins == 0: a1 minus the histogram increment; SDF / weight / colour unchanged."""
     sc = Scenario(dims=(64, 64, 64), bins=16, frames=3)
