@@ -260,6 +260,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the CUDA path")
     torch.cuda.set_device(local)
+    # a non-default stream for everything this process times: kernels on the legacy default stream do not run
+    # concurrently with work on other (blocking) streams, and the library overlaps its preparation kernels with the update
+    torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
