@@ -123,6 +123,10 @@ void sfm_destroy(sfm_volume *v);
  * (end-start)/(dim-1), miu = trunc_voxels*voxel.x, SDF := miu, other planes := 0, n_obs := 0,
  * init_extrinsic_inv := extrinsic^-1.  The frame itself is NOT integrated (tsdf.cu:213). */
 int sfm_init_from_frame(sfm_volume *v, const uint16_t *depth, const float *extrinsic16, float mean_depth);
+/* The placement rule alone (tsdf.cu:180-199), host arithmetic only -- no handle, no device: bounds, voxel size and
+ * truncation distance from the first depth frame.  sfm_init_from_frame is this + sfm_set_bounds. */
+int sfm_place_volume(const uint16_t *depth, int width, int height, const float *Kinv16, float mean_depth,
+	const int32_t *dims3, float trunc_voxels, float *vol_start3, float *vol_end3, float *voxel3, float *miu);
 /* Explicit placement (what the parity tests use so both sides get identical bits). */
 int sfm_set_bounds(sfm_volume *v, const float *vol_start3, const float *vol_end3, const float *voxel3, float miu);
 

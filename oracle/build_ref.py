@@ -132,6 +132,37 @@ def build(bins_list=BINS, verbose=True):
                 print(f"[build_ref] built {so}")
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+    build_tsdf_python(verbose)
+    return True
+
+
+def build_tsdf_python(verbose=True):
+    """Secondary oracle: the TSDF_Python prototype's CUDA module (src/TSDF_Python/tsdf.cu:10-58 kernel, :61-137 host
+    wrapper, tsdf.cpp:11-38 pybind11 binding), compiled VERBATIM from where the two files lie into
+    oracle/_ref/tsdf_cuda<ext>.  Its CMakeLists only sets -std=c++11 and links CUDA + Python; the build system itself
+    is not run (it asks for FindCUDA and a pybind11 CMake package).  nvcc 12.9 needs c++14 for thrust, so the flag is
+    -std=c++14; no other option is added (default -fmad=true, as the reference)."""
+    import sysconfig
+    src = os.path.join(os.path.dirname(REF), "TSDF_Python")
+    if not os.path.isfile(os.path.join(src, "tsdf.cu")):
+        return False
+    try:
+        import pybind11
+    except ImportError:
+        if verbose:
+            print("[build_ref] pybind11 missing: TSDF_Python oracle not built")
+        return False
+    ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    so = os.path.join(OUT, "tsdf_cuda" + ext)
+    tmp = tempfile.mkdtemp(prefix="sfm_ref_py_")
+    try:
+        run(["nvcc", "-std=c++14", "-shared", "-Xcompiler", "-fPIC", "-w", f"-I{src}", f"-I{pybind11.get_include()}",
+             f"-I{sysconfig.get_paths()['include']}"] + ARCH +
+            [os.path.join(src, "tsdf.cu"), os.path.join(src, "tsdf.cpp"), "-o", so], tmp)
+        if verbose:
+            print(f"[build_ref] built {so}")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     return True
 
 

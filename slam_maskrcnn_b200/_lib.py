@@ -63,6 +63,7 @@ SYMBOLS = {
     "sfm_create": (_i, [C.POINTER(Desc), C.POINTER(_vp)]),
     "sfm_destroy": (None, [_vp]),
     "sfm_init_from_frame": (_i, [_vp, _vp, _vp, _f]),
+    "sfm_place_volume": (_i, [_vp, _i, _i, _vp, _f, _vp, _f, _vp, _vp, _vp, _vp]),
     "sfm_set_bounds": (_i, [_vp, _vp, _vp, _vp, _f]),
     "sfm_parse_frame": (_i, [_vp, _vp, _vp, _vp, _vp, _f]),
     "sfm_fuse_frame": (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -1112,35 +1112,45 @@ int sfm_set_bounds(sfm_volume *v, const float *vol_start3, const float *vol_end3
 	return reset_planes(v);
 }
 
-int sfm_init_from_frame(sfm_volume *v, const uint16_t *depth, const float *extrinsic16, float mean_depth) {
-	if (!v || !depth || !extrinsic16) return fail(SFM_ERR_INVALID, "null argument");
+int sfm_place_volume(const uint16_t *depth, int width, int height, const float *Kinv16, float mean_depth, const int32_t *dims3,
+	float trunc_voxels, float *vol_start3, float *vol_end3, float *voxel3, float *miu)
+{
+	if (!depth || !Kinv16 || !dims3 || !vol_start3 || !vol_end3 || !voxel3 || !miu || width <= 0 || height <= 0)
+		return fail(SFM_ERR_INVALID, "null argument");
 	// tsdf.cu:180-182: bounding rectangle of depth != 0 (the saturating cast to u8 keeps nonzero nonzero)
-	int x0 = v->W, y0 = v->H, x1 = -1, y1 = -1;
-	for (int y = 0; y < v->H; y++)
-		for (int x = 0; x < v->W; x++)
-			if (depth[(size_t)y * v->W + x]) { x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y); }
+	int x0 = width, y0 = height, x1 = -1, y1 = -1;
+	for (int y = 0; y < height; y++)
+		for (int x = 0; x < width; x++)
+			if (depth[(size_t)y * width + x]) { x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y); }
 	if (x1 < 0) return fail(SFM_ERR_INVALID, "first depth frame has no valid pixel");
 	// cv::Rect: tl = (x0,y0), br = (x0+width, y0+height) = (x1+1, y1+1)
 	const float tlp[4] = {(float)x0, (float)y0, 1.f, 1.f}, brp[4] = {(float)(x1 + 1), (float)(y1 + 1), 1.f, 1.f};
 	float tl[4], br[4];
-	for (int r = 0; r < 4; r++) {  // tsdf.cu:185-188  Kinv(4x4) * p, then * mean_depth
+	for (int r = 0; r < 4; r++) {  // tsdf.cu:185-188  Kinv(4x4) * p (cv::Mat float gemm: double accumulation), then * mean_depth
 		double a = 0, b = 0;
-		for (int k = 0; k < 4; k++) { a += (double)v->Kinv[r * 4 + k] * tlp[k]; b += (double)v->Kinv[r * 4 + k] * brp[k]; }
+		for (int k = 0; k < 4; k++) { a += (double)Kinv16[r * 4 + k] * tlp[k]; b += (double)Kinv16[r * 4 + k] * brp[k]; }
 		tl[r] = (float)a * mean_depth;
 		br[r] = (float)b * mean_depth;
 	}
 	// tsdf.cu:193: sqrt(pow(dx,2)+pow(dy,2))/2 evaluated in double, stored to float
 	const float half_side = (float)(sqrt(pow((double)(tl[0] - br[0]), 2) + pow((double)(tl[1] - br[1]), 2)) / 2);
-	float start[3], end[3], voxel[3];
-	const int dims[3] = {v->g.Dx, v->g.Dy, v->g.Dz};
 	for (int a = 0; a < 3; a++) {
 		const float center = (tl[a] + br[a]) / 2;      // tsdf.cu:194
-		start[a] = center - half_side;                 // tsdf.cu:195
-		end[a] = center + half_side;                   // tsdf.cu:196
-		voxel[a] = (end[a] - start[a]) / (float)(dims[a] - 1);  // tsdf.cu:197 (cv::divide in f32)
+		vol_start3[a] = center - half_side;            // tsdf.cu:195
+		vol_end3[a] = center + half_side;              // tsdf.cu:196
+		voxel3[a] = (vol_end3[a] - vol_start3[a]) / (float)(dims3[a] - 1);  // tsdf.cu:197 (cv::divide in f32)
 	}
-	const float miu = v->desc.trunc_voxels * voxel[0];  // tsdf.cu:199
-	int rc = sfm_set_bounds(v, start, end, voxel, miu);
+	*miu = trunc_voxels * voxel3[0];                   // tsdf.cu:199
+	return SFM_OK;
+}
+
+int sfm_init_from_frame(sfm_volume *v, const uint16_t *depth, const float *extrinsic16, float mean_depth) {
+	if (!v || !depth || !extrinsic16) return fail(SFM_ERR_INVALID, "null argument");
+	float start[3], end[3], voxel[3], miu = 0.f;
+	const int32_t dims[3] = {v->g.Dx, v->g.Dy, v->g.Dz};
+	int rc = sfm_place_volume(depth, v->W, v->H, v->Kinv, mean_depth, dims, v->desc.trunc_voxels, start, end, voxel, &miu);
+	if (rc) return rc;
+	rc = sfm_set_bounds(v, start, end, voxel, miu);
 	if (rc) return rc;
 	v->mean_depth = mean_depth;                         // tsdf.cu:191
 	if (!mat4_inv(extrinsic16, v->init_extr_inv)) return fail(SFM_ERR_INVALID, "singular first extrinsic");  // tsdf.cu:177

@@ -25,6 +25,21 @@ def _f32(a, n):
     return a
 
 
+def place_volume(depth, Kinv, mean_depth, dims, trunc_voxels=5.0):
+    """sfm_place_volume: the reference's volume placement rule (tsdf.cu:180-199) -> (start, end, voxel, miu), float32.
+    Host arithmetic only (no GPU needed)."""
+    from . import _lib
+    lib = _lib.load()
+    depth = np.ascontiguousarray(depth, np.uint16)
+    h, w = depth.shape
+    start, end, voxel = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    miu = C.c_float(0)
+    d = np.ascontiguousarray(dims, np.int32)
+    check(lib.sfm_place_volume(_ptr(depth), w, h, _ptr(_f32(Kinv, 16)), C.c_float(float(mean_depth)), _ptr(d), C.c_float(trunc_voxels),
+                               _ptr(start), _ptr(end), _ptr(voxel), C.byref(miu)))
+    return start, end, voxel, np.float32(miu.value)
+
+
 def intrinsic_matrix(fx, fy, cx, cy):
     """tsdf.cu:137-146: eye(4) float32 with fx, fy, cx, cy."""
     K = np.eye(4, dtype=np.float32)
