@@ -174,6 +174,10 @@ int sfm_overlap_tables(sfm_volume *v, const float *extrinsic2init16, const uint8
 int sfm_merge_decide(sfm_volume *v, const double *A, const uint32_t *C, uint8_t *mask_inout,
 	sfm_merge_report *report);
 int sfm_last_merge(sfm_volume *v, sfm_merge_report *report);
+/* `num_objs` is a public member of the reference's TSDF (tsdf.cuh:58): the count of global instance ids handed out so
+ * far, from which the merge numbers new instances (tsdf.cu:383).  sfm_get_info reads it; this sets it (parity hook:
+ * the raw integrate entry points do not maintain it). */
+int sfm_set_num_objs(sfm_volume *v, int num_objs);
 
 /* Planes in the reference layout / dtypes (the getters get_tsdf_diff/color/cnt, tsdf.cu:506-516,
  * return stale host mirrors in the reference; these copy the live device planes).

@@ -49,6 +49,10 @@ struct Mat {
 		return *this;
 	}
 	bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+#ifdef SFM_WITH_OPENCV
+	// `cv::Mat img = viewer->show_tsdf(...)` as in the reference's kernel.cpp:105 (8-bit images only)
+	operator cv::Mat() const { return cv::Mat(rows, cols, CV_8UC(channels), data).clone(); }
+#endif
 };
 
 inline void check(int rc) {

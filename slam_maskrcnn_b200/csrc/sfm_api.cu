@@ -1224,6 +1224,12 @@ int sfm_merge_decide(sfm_volume *v, const double *A, const uint32_t *C, uint8_t 
 	return SFM_OK;
 }
 
+int sfm_set_num_objs(sfm_volume *v, int num_objs) {
+	if (!v || num_objs < 0) return fail(SFM_ERR_INVALID, "bad argument");
+	v->num_objs = num_objs;
+	return SFM_OK;
+}
+
 int sfm_last_merge(sfm_volume *v, sfm_merge_report *report) {
 	if (!v || !report) return fail(SFM_ERR_INVALID, "null argument");
 	*report = v->last_merge;

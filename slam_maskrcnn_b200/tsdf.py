@@ -294,6 +294,9 @@ class Volume:
     def synchronize(self):
         check(self.lib.sfm_synchronize(self._h))
 
+    def set_num_objs(self, n):
+        check(self.lib.sfm_set_num_objs(self._h, int(n)))
+
     def wait_uploads(self):
         """Blocks until every frame copy issued so far has read its source buffers (FLAG_ASYNC_SOURCES)."""
         check(self.lib.sfm_wait_uploads(self._h))

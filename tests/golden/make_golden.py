@@ -72,7 +72,8 @@ def main():
                     [np.sin(angle), 0, np.cos(angle), dist - dist * np.cos(angle)], [0, 0, 0, 1]], np.float32)
     s2w = (rot.astype(np.float64) @ sc.Kinv.astype(np.float64)).astype(np.float32)
     c3 = np.array([(dist + 0.5) * np.sin(angle), 0, (dist + 0.5) - (dist + 0.5) * np.cos(angle)], np.float32)
-    pal = np.tile(np.array([[230, 25, 75], [60, 180, 75], [255, 225, 25], [0, 130, 200]], np.uint8), (4, 1))
+    from slam_maskrcnn_b200 import palette
+    pal = palette(bins)  # the reference's own 16 colours (viewer.cu:93-109), what sfm_show uses
     img = torch.zeros(sc.H * sc.W * 3, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ob.ref_show(bins, s2w, c3, sc.start, sc.end, sc.voxel, sc.dims, sdf_p, col_p, cnt_p, sc.W, sc.H, img.data_ptr(), pal)

@@ -191,3 +191,27 @@ def test_write_ply_layout(tmp_path):
     write_ply(str(p), xyz, bgr)  # without labels: 15-byte records
     raw = p.read_bytes()
     assert len(raw) - (raw.index(b"end_header\n") + 11) == 17 * 15
+
+
+def test_opencv_overloads_compile(tmp_path):
+    """include/sfm_b200.hpp under SFM_WITH_OPENCV (the cv::Scalar constructor, parse_frame(cv::Mat...), the cv::Mat
+    conversion of the rendered image): compiled against a stub <opencv2/core.hpp> with OpenCV's signatures
+    (tests/stubs), used the way the reference's kernel.cpp:40,99,105 uses them.  OpenCV C++ is not in this image, so
+    this is a syntax / overload-resolution check, not a link."""
+    import subprocess
+    src = tmp_path / "use_opencv_overloads.cpp"
+    src.write_text(r"""
+#define SFM_WITH_OPENCV
+#include "sfm_b200.hpp"
+int run(cv::Mat depth, cv::Mat color, cv::Mat mask, cv::Mat extrinsic, float mean_depth) {
+	TSDF *tsdf = new TSDF(cv::Scalar(520.9, 521.0, 325.1, 249.7));      // kernel.cpp:39-40
+	tsdf->parse_frame(depth, color, mask, extrinsic, mean_depth);       // kernel.cpp:99
+	Viewer *viewer = new Viewer(depth.cols, depth.rows);
+	cv::Mat img = viewer->show_tsdf(*tsdf, 0.01f, tsdf->mean_depth_);   // kernel.cpp:105
+	return img.rows;
+}
+""")
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-I", os.path.join(ROOT, "tests", "stubs"), str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout

@@ -29,22 +29,20 @@ def test_cuda_path_reproduces_reference_outputs():
     gp = g["probs"].reshape(sc.H, sc.W, sc.bins)
     assert (bits(probs)[ok] == bits(gp)[ok]).all()
     assert (box[ok] == g["box_mask"].reshape(sc.H, sc.W, sc.bins)[ok]).all()
-    # merge decision + relabel through the fused path
+    # merge decision + relabel through the fused tables: the whole relabelled mask and num_objs
     mask = g["merge_mask_in"].copy()
     A, C = v.overlap_tables(sc.frames[3]["extrinsic"], mask)
-    info0 = v.info()
-    # num_objs before the merge is max(gt of first frame)+1 in the fixture
-    import ctypes
+    v.set_num_objs(int(g["merge_num_objs"][0]))  # TSDF::num_objs before the merge, as the fixture's run had it
     rep = v.merge_decide(A, C, mask)
-    # sfm_merge_decide starts from the handle's num_objs (0 here: integrate_raw does not set it), so compare labels
-    # of matched instances only; new ids are covered by test_fuse_frame_pipeline_matches_reference
-    matched = np.isin(g["merge_mask_out"], np.unique(g["merge_mask_out"])[np.unique(g["merge_mask_out"]) < int(g["merge_num_objs"][0])])
-    assert (mask[matched] == g["merge_mask_out"][matched]).all()
-    # ray-cast
+    assert (mask == g["merge_mask_out"]).all(), f"relabelled mask differs at {int((mask != g['merge_mask_out']).sum())} pixels"
+    assert v.info().num_objs == int(g["merge_num_objs"][1])
+    assert rep.margin > 1e-4
+    # ray-cast: the image, byte for byte, on the rays that needed no boundary clamp (same palette as the fixture)
+    assert (np.asarray(g["show_palette"]).reshape(-1)[:sc.bins * 3] == palette(sc.bins).reshape(-1)).all()
     bgr, _, _ = v.raycast(g["show_s2w"], g["show_c"])
     fl = v.ray_flags()
     gb = g["show_bgr"].reshape(sc.H, sc.W, 3)
-    # fixture palette differs from the library's: compare lit / unlit pattern and labels through the palette index
-    lit, glit = bgr.sum(-1) > 0, gb.sum(-1) > 0
-    assert (lit == glit)[fl == 0].all()
+    ok = fl == 0
+    assert ok.mean() > 0.9 and (gb.sum(-1) > 0).mean() > 0.05
+    assert (bgr[ok] == gb[ok]).all(), f"ray-cast image differs on {int((bgr[ok] != gb[ok]).any(-1).sum())} in-bounds rays"
     v.close()

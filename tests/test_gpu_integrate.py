@@ -182,3 +182,20 @@ def test_thin_slabs_hold_identical_planes(slab):
     v.close()
     assert_planes_equal(part, {k: full[k][:, :, z0:z0 + nz] for k in part}, f"slab {slab} vs whole volume")
     assert part["weight"].sum() > 0
+
+
+@pytest.mark.parametrize("blocks_per_sm", [1, 3])
+def test_results_do_not_depend_on_scheduling(blocks_per_sm, monkeypatch):
+    """Race check by construction (compute-sanitizer is closed on this pool, profiles/r2_sanitizer_*.log): the same
+    sequence with a different number of resident K1b blocks per SM -- a different assignment of bricks to warps, a
+    different interleaving of the surface-queue drains, and a preparation stream that runs further ahead -- and run
+    twice in a row must leave identical planes.  Every voxel is written by exactly one lane per frame and the histogram
+    bins by one reduction per voxel and frame, so any difference would be a race."""
+    sc = Scenario(dims=(96, 96, 96), bins=16, frames=6, yaw_step_deg=4.0)
+    a, sa = run_ours(sc)
+    a2, sa2 = run_ours(sc)
+    monkeypatch.setenv("SFM_K1B_BLOCKS_PER_SM", str(blocks_per_sm))
+    b, sb = run_ours(sc)
+    assert_planes_equal(a, a2, "run to run")
+    assert_planes_equal(a, b, f"{blocks_per_sm} K1b blocks per SM vs default")
+    assert sa == sa2 == sb

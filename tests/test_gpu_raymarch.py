@@ -230,6 +230,42 @@ def test_raycast_close_to_cpu_oracle():
     v.close()
 
 
+def test_clamped_rays_follow_the_documented_contract():
+    """Rays whose trilinear taps would leave the volume: the reference reads out of bounds there (utils.cu:103-112, SURVEY
+    appendix B.2), so they are flagged and excluded from the bit-exact comparisons above.  By geometry this needs a
+    sample whose floor index is exactly D-1, i.e. a sample ON a high face (the marcher samples inside
+    [tnear + 1e-6, tfar - 1e-6]), so flagged rays are a corner case: this test states that (< 0.1 % of the rays, even
+    for a cube cut out of the middle of the scene, whose surfaces leave it through every face), and that on such a
+    cube the whole image -- flagged rays included -- follows the clamp-to-edge contract of sfm_b200.h, which the CPU
+    oracle implements too (tolerance level: ray directions go through MUFU.RSQ on the GPU)."""
+    from slam_maskrcnn_b200 import orbit_camera, palette
+    sc = Scenario(dims=(64, 64, 64), bins=16, frames=5, yaw_step_deg=2.0)
+    lo, hi = sc.start.astype(np.float64), sc.end.astype(np.float64)
+    sc.start = (lo + 0.22 * (hi - lo)).astype(np.float32)
+    sc.end = (hi - 0.22 * (hi - lo)).astype(np.float32)
+    sc.voxel = ((sc.end - sc.start) / (np.array(sc.dims, np.float32) - np.float32(1))).astype(np.float32)
+    sc.miu = np.float32(5) * sc.voxel[0]
+    v = sc.make_volume()
+    cv = sc.make_cpu_volume()
+    for fr in sc.frames:
+        v.integrate_raw(fr["depth"], fr["color"], fr["gt"], fr["extrinsic"])
+        cv.integrate(sc.K, fr["depth"], fr["color"], fr["gt"], fr["extrinsic"], sc.W, sc.H)
+    for angle in (0.05, 0.3, 0.6):
+        s2w, c = orbit_camera(sc.Kinv, angle, float(sc.mean_depth))
+        bgr, t, lab = v.raycast(s2w, c, want_t=True, want_label=True)
+        flags = v.ray_flags()
+        obgr, ot, olab = cv.raycast(s2w, c, sc.W, sc.H, palette(16))
+        assert (flags != 0).mean() < 1e-3
+        assert ((t > 0) == (ot > 0)).mean() > 0.99, "hit / miss pattern"
+        both = (t > 0) & (ot > 0)
+        assert both.mean() > 0.2 and (lab == olab)[both].mean() > 0.99
+        np.testing.assert_allclose(t[both], ot[both], rtol=2e-3)
+        cl = (flags != 0) & both
+        if cl.any():
+            assert (lab == olab)[cl].mean() > 0.9
+    v.close()
+
+
 def test_invariant_divisor_division_is_ieee_exact():
     """div_by() (k_raymarch.cuh) must equal the IEEE divide bit for bit: 3 x 2^24 pseudo-random operands per divisor."""
     import ctypes as C
