@@ -198,6 +198,25 @@ int sfm_planes_written(sfm_volume *v);
  * sfm_hist_export_dev writes the same into a caller-owned device buffer of sfm_plane_bytes(SFM_PLANE_HIST) bytes,
  * ordered on the handle's stream. */
 int sfm_hist_export_dev(sfm_volume *v, void *d_dst_u32);
+/* Ray-cast of a z-slab-sharded volume AFTER the fusion is over (the viewer runs after the frame loop, kernel.cpp:101-107):
+ * the SDF (4 bytes per voxel) is replicated, the histogram (2 x bins bytes per voxel) stays sharded.
+ *   sfm_sdf_planes_dev    copies global planes [z0, z0+n) of the SDF between a handle and a packed device buffer
+ *                         [Dx][Dy][n] (to_buffer != 0: export, e.g. a slab's owned planes; 0: import into a replica)
+ *   sfm_rebuild_skip_map  recomputes the marcher's surface-block map from the SDF plane as it is now
+ *   sfm_raycast_band_dev  marches the rays of image rows [row0, row0+rows) on a full-volume handle (a bins = 0 replica
+ *                         will do) and writes their hits {x, y, z, t} (t == 0: no hit) into d_hits f32[h*w*4]
+ *   sfm_label_hits_dev    on a slab handle: arg-max label (viewer.cu:69-79) of the hits whose sample lies in the OWNED
+ *                         planes -> d_keys u64[h*w] = float_bits(t) << 32 | label, SFM_NO_HIT_KEY elsewhere; a MIN
+ *                         over the ranks gives the single-volume keys.
+ * The march on the replica is the single-volume march (same kernel, same SDF bits), so the composite equals
+ * sfm_raycast_keys_dev on one big volume bit for bit. */
+int sfm_sdf_planes_dev(sfm_volume *v, int z0, int n, void *d_buf, int to_buffer);
+int sfm_rebuild_skip_map(sfm_volume *v);
+int sfm_raycast_band_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, int row0, int rows, void *d_hits);
+int sfm_label_hits_dev(sfm_volume *v, const void *d_hits, int w, int h, void *d_keys);
+/* SDF samples gathered (8 taps x 4 bytes each) and surface hits of the ray marches since the previous call: the
+ * algorithmic bytes of the ray kernels. */
+int sfm_ray_stats(sfm_volume *v, uint64_t *samples, uint64_t *hits);
 /* Blocks until every frame copy issued so far has read its source buffers (see SFM_FLAG_ASYNC_SOURCES). */
 int sfm_wait_uploads(sfm_volume *v);
 

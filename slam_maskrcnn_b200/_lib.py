@@ -92,6 +92,11 @@ SYMBOLS = {
     "sfm_wait_uploads": (_i, [_vp]),
     "sfm_planes_written": (_i, [_vp]),
     "sfm_hist_export_dev": (_i, [_vp, _vp]),
+    "sfm_sdf_planes_dev": (_i, [_vp, _i, _i, _vp, _i]),
+    "sfm_rebuild_skip_map": (_i, [_vp]),
+    "sfm_raycast_band_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sfm_label_hits_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sfm_ray_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_set_stream": (_i, [_vp, _vp]),
     "sfm_timer_start": (_i, [_vp]),
     "sfm_timer_stop": (_i, [_vp, C.POINTER(_f)]),

@@ -125,6 +125,8 @@ struct sfm_volume {
 	cudaEvent_t ev_call = nullptr;
 	size_t tile_bytes = 0;
 	unsigned long long *d_stats = nullptr;
+	unsigned long long *d_ray_stats = nullptr;  // [0] SDF samples gathered, [1] hits, cumulative (march_kernel)
+	uint64_t ray_samples_seen = 0, ray_hits_seen = 0;
 	uint32_t *d_err = nullptr;
 	size_t nbricks = 0;
 	int num_sms = 148;
@@ -616,7 +618,7 @@ int enqueue_march_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	const int npix = v->W * v->H;
 	int rc = ensure_ray_buffers(v, (size_t)npix, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr);
+	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr, 0, v->H, v->d_ray_stats);
 	LAUNCH_CHECK(v);
 	return launch_fold(v, v->d_fold, d_mask, nullptr, 1);
 }
@@ -983,6 +985,8 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
+	CU_OR_DESTROY(cudaMalloc(&v->d_ray_stats, 16));
+	CU_OR_DESTROY(cudaMemset(v->d_ray_stats, 0, 16));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
 	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
 		// brick shape on the 128-bit path: 32 planes per brick unless the slab is so thin that more than half the lanes
@@ -1067,6 +1071,7 @@ void sfm_destroy(sfm_volume *v) {
 	}
 	if (v->ev_call) cudaEventDestroy(v->ev_call);
 	cudaFree(v->d_stats);
+	cudaFree(v->d_ray_stats);
 	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);
@@ -1317,7 +1322,7 @@ int sfm_backproject(sfm_volume *v, const float *E16, float *probs, uint8_t *box_
 	if (rc) return rc;
 	CU(cudaMemsetAsync(v->d_probs, 0, npx * v->bins * 4, v->stream));  // tsdf.cu:428-429
 	CU(cudaMemsetAsync(v->d_box, 0, npx * v->bins, v->stream));
-	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16), v->d_hits, v->d_flags);
+	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16), v->d_hits, v->d_flags, 0, v->H, v->d_ray_stats);
 	LAUNCH_CHECK(v);
 	probs_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->desc.presence_thresh,
 		v->d_probs, v->d_box, v->d_t, v->d_flags);
@@ -1338,10 +1343,10 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	if (rc) return rc;
 	rc = ensure_ray_buffers(v, (size_t)w * h, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr);
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr, 0, h, v->d_ray_stats);
 	LAUNCH_CHECK(v);
 	shade_kernel<<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
-		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr);
+		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 0);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
 }
@@ -1355,10 +1360,10 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	const size_t npx = (size_t)w * h;
 	rc = ensure_ray_buffers(v, npx, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags);
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h, v->d_ray_stats);
 	LAUNCH_CHECK(v);
 	shade_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
-		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags);
+		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags, 0);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));  // viewer.cu:167
 	if (t_opt) CU(cudaMemcpyAsync(t_opt, v->d_t, npx * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -1376,7 +1381,7 @@ int sfm_raycast_color(sfm_volume *v, const float *s2w16, const float *c3, int w,
 	const size_t npx = (size_t)w * h;
 	rc = ensure_ray_buffers(v, npx, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags);
+	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h, v->d_ray_stats);
 	LAUNCH_CHECK(v);
 	shade_color_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), v->planes.color, (int)npx, v->d_hits, v->d_bgr, v->d_t);
 	LAUNCH_CHECK(v);
@@ -1521,6 +1526,66 @@ int sfm_keys_to_bgr(sfm_volume *v, const void *d_keys, int w, int h, uint8_t *bg
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));
 	CU(cudaStreamSynchronize(v->stream));
+	return SFM_OK;
+}
+
+/* ---- ray-cast of a z-slab-sharded volume with a replicated SDF (viewer.cu:137-179 after the fusion is over) ---- */
+
+int sfm_sdf_planes_dev(sfm_volume *v, int z0, int n, void *d_buf, int to_buffer) {
+	if (!v || !d_buf || n <= 0) return fail(SFM_ERR_INVALID, "bad argument");
+	if (z0 < v->g.z0 || z0 + n > v->g.z0 + v->g.nz) return fail(SFM_ERR_INVALID, "planes outside the range this handle stores");
+	CU(cudaSetDevice(v->desc.device));
+	sdf_planes_kernel<<<v->num_sms * 16, 256, 0, v->stream>>>(v->g, v->planes.sdf, z0, n, (float *)d_buf, to_buffer ? 1 : 0);
+	LAUNCH_CHECK(v);
+	if (!to_buffer) {  // the SDF changed under the skip map and the steady knowledge
+		CU(cudaMemsetAsync(v->planes.occ, 1, v->occ_bytes, v->stream));
+	}
+	return SFM_OK;
+}
+
+int sfm_rebuild_skip_map(sfm_volume *v) {
+	if (!v) return fail(SFM_ERR_INVALID, "null argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	CU(cudaMemsetAsync(v->planes.occ, 0, v->occ_bytes, v->stream));
+	rebuild_skip_map_kernel<<<v->num_sms * 16, 128, 0, v->stream>>>(v->g, v->planes.sdf, v->planes.occ);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+int sfm_raycast_band_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, int row0, int rows, void *d_hits) {
+	if (!v || !s2w16 || !c3 || !d_hits || w <= 0 || h <= 0 || row0 < 0 || rows <= 0 || row0 + rows > h) return fail(SFM_ERR_INVALID, "bad argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_raycast_band_dev");
+	if (rc) return rc;
+	march_kernel<<<ray_blocks(w, rows), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), (float4 *)d_hits, nullptr,
+		row0, rows, v->d_ray_stats);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+int sfm_label_hits_dev(sfm_volume *v, const void *d_hits, int w, int h, void *d_keys) {
+	if (!v || !d_hits || !d_keys || w <= 0 || h <= 0) return fail(SFM_ERR_INVALID, "bad argument");
+	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
+	CU(cudaSetDevice(v->desc.device));
+	const int npx = w * h;
+	shade_kernel<<<(npx + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), npx, (const float4 *)d_hits, v->d_palette,
+		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1);
+	LAUNCH_CHECK(v);
+	return SFM_OK;
+}
+
+int sfm_ray_stats(sfm_volume *v, uint64_t *samples, uint64_t *hits) {
+	if (!v || !samples || !hits) return fail(SFM_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(v->desc.device));
+	unsigned long long h2[2] = {0, 0};
+	CU(cudaMemcpyAsync(h2, v->d_ray_stats, 16, cudaMemcpyDeviceToHost, v->stream));
+	CU(cudaStreamSynchronize(v->stream));
+	*samples = h2[0] - v->ray_samples_seen;
+	*hits = h2[1] - v->ray_hits_seen;
+	v->ray_samples_seen = h2[0];
+	v->ray_hits_seen = h2[1];
 	return SFM_OK;
 }
 

@@ -262,6 +262,60 @@ class SlabVolume:
         composite_keys(keys, group)
         return keys
 
+    # ---- ray-cast after the fusion: SDF replicated, histogram sharded (config 4) -----------------------
+    def build_sdf_replica(self, plan, bounds, K=None, Kinv=None, group=None):
+        """All-gathers the owned SDF planes of every rank's slab into a full-volume, label-free handle on THIS rank
+        (4 bytes per voxel: 4.3 GB at 1024^3) and rebuilds its skip map.  `plan`: [(z0, nz)] of all ranks; `bounds`:
+        (start, end, voxel, miu) of the volume.  Call once after the last frame (the reference's viewer runs after
+        its frame loop, kernel.cpp:101-107); call again if more frames are fused."""
+        import torch
+        import torch.distributed as dist
+        from .tsdf import Volume
+        v = self.vol
+        dev = torch.device("cuda", v.desc.device)
+        dims = tuple(v.dims)
+        if getattr(self, "replica", None) is None:
+            self.replica = Volume(dims=dims, bins=0, width=self.width, height=self.height, device=v.desc.device, K=K, Kinv=Kinv)
+            self.replica.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            self.replica.set_bounds(*bounds)
+        self.plan = list(plan)
+        cols = dims[0] * dims[1]
+        nmax = max(n for _, n in plan)
+        mine = torch.empty(cols * nmax, dtype=torch.float32, device=dev)
+        v.sdf_planes_dev(self.z0, self.nz, mine.data_ptr(), True)
+        if self.world > 1 and dist.is_initialized():
+            everyone = torch.empty(self.world * cols * nmax, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+        else:
+            everyone = mine
+        for r, (z0, n) in enumerate(plan):
+            self.replica.sdf_planes_dev(z0, n, everyone.data_ptr() + r * cols * nmax * 4, False)
+        self.replica.rebuild_skip_map()
+        return self.replica
+
+    def raycast_replicated(self, s2w, c, w, h, group=None):
+        """One view on the replicated SDF: this rank marches its band of image rows (the single-volume march: same
+        kernel, same SDF bits), the hit positions are all-gathered (16 bytes per ray), every rank labels the hits
+        that fall into the planes it owns, and one MIN all-reduce composites the keys.  Two collectives per view,
+        no ray is marched twice.  Returns the composited int64 key image (identical on every rank)."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.vol.desc.device)
+        rows = (h + self.world - 1) // self.world          # band height (the last band may be shorter)
+        hits = torch.zeros(self.world * rows * w * 4, dtype=torch.float32, device=dev)
+        row0 = self.rank * rows
+        nrows = max(0, min(rows, h - row0))
+        band = hits[row0 * w * 4:(row0 + rows) * w * 4]
+        if nrows > 0:
+            # the band kernel writes at image coordinates, so hand it a pointer shifted back to row 0 of the image
+            self.replica.raycast_band_dev(s2w, c, w, h, row0, nrows, hits.data_ptr())
+        if self.world > 1 and dist.is_initialized():
+            dist.all_gather_into_tensor(hits, band.clone(), group=group)
+        keys = torch.empty(w * h, dtype=torch.int64, device=dev)
+        self.vol.label_hits_dev(hits.data_ptr(), w, h, keys.data_ptr())
+        composite_keys(keys, group)
+        return keys
+
     def set_bounds(self, *a, **k):
         self.vol.set_bounds(*a, **k)
 
@@ -318,4 +372,7 @@ class SlabVolume:
         return lut, rep
 
     def close(self):
+        if getattr(self, "replica", None) is not None:
+            self.replica.close()
+            self.replica = None
         self.vol.close()

@@ -294,6 +294,23 @@ class Volume:
     def synchronize(self):
         check(self.lib.sfm_synchronize(self._h))
 
+    def sdf_planes_dev(self, z0, n, d_buf, to_buffer):
+        check(self.lib.sfm_sdf_planes_dev(self._h, int(z0), int(n), C.c_void_p(d_buf), 1 if to_buffer else 0))
+
+    def rebuild_skip_map(self):
+        check(self.lib.sfm_rebuild_skip_map(self._h))
+
+    def raycast_band_dev(self, s2w, c, w, h, row0, rows, d_hits):
+        check(self.lib.sfm_raycast_band_dev(self._h, _ptr(_f32(s2w, 16)), _ptr(_f32(c, 3)), w, h, int(row0), int(rows), C.c_void_p(d_hits)))
+
+    def label_hits_dev(self, d_hits, w, h, d_keys):
+        check(self.lib.sfm_label_hits_dev(self._h, C.c_void_p(d_hits), w, h, C.c_void_p(d_keys)))
+
+    def ray_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.lib.sfm_ray_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_num_objs(self, n):
         check(self.lib.sfm_set_num_objs(self._h, int(n)))
 
