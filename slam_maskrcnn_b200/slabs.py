@@ -247,6 +247,17 @@ class SlabVolume:
         except ImportError:
             pass
 
+    @classmethod
+    def wrap(cls, vol, rank, world, own, width=FRAME_W, height=FRAME_H):
+        """A SlabVolume around an existing slab handle (`own` = (z0, nz) of the planes it owns)."""
+        self = cls.__new__(cls)
+        self.rank, self.world = rank, world
+        self.z0, self.nz = own
+        self.vol = vol
+        self.width, self.height = width, height
+        self.replica = None
+        return self
+
     def raycast_sharded(self, s2w, c, w, h, group=None):
         """Exact sharded ray-cast: returns the composited int64 key image (CUDA tensor, identical on every rank)."""
         import torch
