@@ -364,14 +364,14 @@ def multi_gpu_parity(rank, world, local, K, Kinv, frames, packed_dev, torch, dis
     from slam_maskrcnn_b200 import Volume, orbit_camera, synth
     from slam_maskrcnn_b200 import slabs as sm
     dims = (128, 128, 32 * world)
-    bins = 16
+    bins = 48  # the bench scene carries labels up to N_INSTANCES = 40
     f0 = frames[0]
     md = synth.mean_depth(f0["depth"])
     place = synth.place_volume(f0["depth"], Kinv, md, dims)
     plan = sm.plan_slabs(dims[2], world)
     own = plan[rank]
     halo = sm.shard_halo(place[2])
-    sz0, snz = sm.stored_range(own[0], own[1], dims[2], halo)
+    sz0, snz = sm.stored_range(own[0], own[1], dims[2], halo, align=4)
     cur = torch.cuda.current_stream().cuda_stream
     slab = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=(sz0, snz), own=own)
     whole = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local)
@@ -509,7 +509,7 @@ def run_ours(args):
         from slam_maskrcnn_b200 import FLAG_ASYNC_SOURCES
         # N > 1: the slab is stored with the halo the sharded ray-cast needs (a few planes on both sides of the owned
         # range, integrated redundantly, never exchanged)
-        stored = slabs_mod.stored_range(plan[rank][0], plan[rank][1], dims[2], halo) if world > 1 else plan[rank]
+        stored = slabs_mod.stored_range(plan[rank][0], plan[rank][1], dims[2], halo, align=8) if world > 1 else plan[rank]
         v = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=stored, own=plan[rank],
                    flags=args.flags | FLAG_ASYNC_SOURCES)
         v.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -736,9 +736,13 @@ def run_ours(args):
                 ray["rays_per_s"] = ray["width"] * ray["height"] / (ray["ms_per_view"] * 1e-3)
                 sv.replica.close()
                 sv.replica = None
-                parity = multi_gpu_parity(rank, world, local, K, Kinv, frames, packed_dev, torch, dist)
         except Exception as e:  # reported, never hidden
             ray = {"error": repr(e)}
+        if world > 1:
+            try:
+                parity = multi_gpu_parity(rank, world, local, K, Kinv, frames, packed_dev, torch, dist)
+            except Exception as e:
+                parity = {"planes_equal": False, "keys_equal": False, "error": repr(e)}
     # ---- secondary workloads (N = 1): spec-conformant inputs, BASELINE configs 1 and 0 -------------------------
     if world == 1 and not args.no_extras:
         try:

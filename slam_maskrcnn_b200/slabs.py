@@ -220,10 +220,15 @@ def shard_halo(voxel):
     return int(np.ceil(float(voxel[0]) / float(voxel[2]))) + 2
 
 
-def stored_range(z0, nz, dz, halo):
-    """Owned planes [z0, z0+nz) -> stored planes including the halo, clipped to the volume."""
+def stored_range(z0, nz, dz, halo, align=1):
+    """Owned planes [z0, z0+nz) -> stored planes including the halo, clipped to the volume.  `align` > 1 rounds the
+    stored range outwards to multiples of `align` planes (a stored plane count that is a multiple of 4 keeps the
+    integrate kernels on their 128-bit path; a multiple of 8 also keeps whole bricks)."""
     lo = max(0, z0 - halo)
     hi = min(dz, z0 + nz + halo)
+    if align > 1:
+        lo = (lo // align) * align
+        hi = min(dz, -(-hi // align) * align)
     return lo, hi - lo
 
 
