@@ -7,7 +7,7 @@ LIB       := $(PKG)/libsfm_b200.so
 CSRC      := $(PKG)/csrc/sfm_api.cu
 CHDR      := $(wildcard $(PKG)/csrc/*.cuh) include/sfm_b200.h
 
-all: $(LIB) oracle/liboracle.so driver/sfm_driver
+all: $(LIB) oracle/liboracle.so driver/sfm_driver driver/sfm_driver_mgpu
 
 $(LIB): $(CSRC) $(CHDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)
@@ -16,13 +16,18 @@ $(LIB): $(CSRC) $(CHDR)
 oracle/liboracle.so: oracle/sfm_oracle.c
 	gcc -O2 -fPIC -shared -ffp-contract=off -mfma -fopenmp -o $@ $< -lm
 
-driver/sfm_driver: driver/kernel.cpp include/sfm_b200.hpp include/sfm_b200.h $(LIB)
-	g++ -O2 -std=c++17 -Iinclude -o $@ driver/kernel.cpp -L$(PKG) -lsfm_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lz
+driver/sfm_driver: driver/kernel.cpp driver/tum_io.hpp include/sfm_b200.hpp include/sfm_b200.h $(LIB)
+	g++ -O2 -std=c++17 -pthread -Iinclude -o $@ driver/kernel.cpp -L$(PKG) -lsfm_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lz
+
+# the same driver over N GPUs of one box, NCCL called from C++ (system libnccl)
+driver/sfm_driver_mgpu: driver/kernel_mgpu.cpp driver/tum_io.hpp include/sfm_b200.hpp include/sfm_b200.h $(LIB)
+	g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include -o $@ driver/kernel_mgpu.cpp -L$(PKG) -lsfm_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' \
+		-L/usr/local/cuda/lib64 -lcudart -lnccl -lz
 
 ref:
 	python oracle/build_ref.py
 
 clean:
-	rm -f $(LIB) oracle/liboracle.so driver/sfm_driver
+	rm -f $(LIB) oracle/liboracle.so driver/sfm_driver driver/sfm_driver_mgpu
 
 .PHONY: all ref clean

@@ -7,9 +7,15 @@
 //   * no OpenCV in this image: PNGs are decoded by the small zlib-based reader below, cv::imshow /
 //     waitKey are dropped, the last rendered view is written as a binary PPM instead;
 //   * paths, time window, frame cap, volume size and bin count are command-line arguments whose
-//     defaults are the reference's hard-coded values (kernel.cpp:39-44,60-61,74; tsdf.cuh:4,52).
+//     defaults are the reference's hard-coded values (kernel.cpp:39-44,60-61,74; tsdf.cuh:4,52);
+//   * the depth <-> mask association (kernel.cpp:64-74) is done up front and the three PNGs of frame i+1, i+2 are
+//     decoded by a second thread while frame i is fused (the reference decodes synchronously inside the loop);
+//     the volume is created from the first decoded frame's size, like the reference (tsdf.cu:225), and a frame of
+//     another size is an error instead of an out-of-bounds read.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,122 +24,13 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
-#include <zlib.h>
-
-#include "sfm_b200.hpp"
-
-using namespace std;
-
-// ---- minimal PNG reader: 8/16-bit grey, RGB, grey+alpha, RGBA; non-interlaced -------------------
-static uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
-
-// Returns rows x cols x channels, 8 or 16 bit (host endian).  want_bgr swaps RGB -> BGR like cv::imread.
-static bool read_png(const string &path, sfm::Mat &out, bool want_bgr) {
-	ifstream f(path, ios::binary);
-	if (!f) return false;
-	vector<uint8_t> buf((istreambuf_iterator<char>(f)), istreambuf_iterator<char>());
-	static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-	if (buf.size() < 33 || memcmp(buf.data(), sig, 8)) return false;
-	uint32_t w = 0, h = 0;
-	int depth = 0, ctype = 0, interlace = 0;
-	vector<uint8_t> idat;
-	for (size_t pos = 8; pos + 12 <= buf.size();) {
-		const uint32_t len = be32(&buf[pos]);
-		const char *type = (const char *)&buf[pos + 4];
-		const uint8_t *data = &buf[pos + 8];
-		if (pos + 12 + len > buf.size()) return false;
-		if (!memcmp(type, "IHDR", 4)) { w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12]; }
-		else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
-		else if (!memcmp(type, "IEND", 4)) break;
-		pos += 12 + len;
-	}
-	if (!w || !h || interlace || (depth != 8 && depth != 16)) return false;
-	const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-	if (!ch) return false;
-	const int bpp = ch * depth / 8;
-	const size_t stride = (size_t)w * bpp;
-	vector<uint8_t> raw((stride + 1) * h);
-	uLongf rawlen = raw.size();
-	if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) return false;
-	vector<uint8_t> img(stride * h);
-	for (uint32_t y = 0; y < h; y++) {  // undo the per-row filters
-		const uint8_t ft = raw[y * (stride + 1)];
-		const uint8_t *src = &raw[y * (stride + 1) + 1];
-		uint8_t *dst = &img[y * stride];
-		const uint8_t *up = y ? &img[(y - 1) * stride] : nullptr;
-		for (size_t i = 0; i < stride; i++) {
-			const int a = i >= (size_t)bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
-			int pred = 0;
-			switch (ft) {
-			case 1: pred = a; break;
-			case 2: pred = b; break;
-			case 3: pred = (a + b) >> 1; break;
-			case 4: { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
-			default: break;
-			}
-			dst[i] = (uint8_t)(src[i] + pred);
-		}
-	}
-	const int out_ch = (ch == 2) ? 1 : (ch == 4 ? 3 : ch);
-	out = sfm::Mat((int)h, (int)w, out_ch, depth / 8);
-	for (size_t p = 0; p < (size_t)w * h; p++)
-		for (int c = 0; c < out_ch; c++) {
-			const int sc = (want_bgr && out_ch == 3) ? 2 - c : c;
-			const uint8_t *s = &img[p * bpp + sc * (depth / 8)];
-			if (depth == 8) out.data[p * out_ch + c] = s[0];
-			else ((uint16_t *)out.data)[p * out_ch + c] = (uint16_t)(s[0] << 8 | s[1]);  // PNG is big endian
-		}
-	return true;
-}
-
-static bool write_ppm_bgr(const string &path, const sfm::Mat &img) {
-	ofstream f(path, ios::binary);
-	if (!f) return false;
-	f << "P6\n" << img.cols << " " << img.rows << "\n255\n";
-	for (size_t p = 0; p < (size_t)img.rows * img.cols; p++) {
-		const char rgb[3] = {(char)img.data[p * 3 + 2], (char)img.data[p * 3 + 1], (char)img.data[p * 3]};
-		f.write(rgb, 3);
-	}
-	return true;
-}
-
-// ---- the reference driver's helpers ---------------------------------------------------------------
-// read_trajactory (utils.cu:62-75): key = fmod(ts, 1e5), value = {tx,ty,tz,qx,qy,qz,qw}
-static map<double, vector<double>> read_trajactory(const string &filename) {
-	map<double, vector<double>> result;
-	string line;
-	ifstream infile(filename.c_str());
-	while (getline(infile, line)) {
-		istringstream iss(line);
-		double ts, tx, ty, tz, qx, qy, qz, qw;
-		if (!(iss >> ts >> tx >> ty >> tz >> qx >> qy >> qz >> qw)) continue;
-		result.insert(make_pair(fmod(ts, 1e5), vector<double>{tx, ty, tz, qx, qy, qz, qw}));
-	}
-	return result;
-}
-
-static vector<string> glob_png(const string &dir) {  // cv::glob(dir/*.png), sorted
-	vector<string> out;
-	if (DIR *d = opendir(dir.c_str())) {
-		while (dirent *e = readdir(d)) {
-			const string n = e->d_name;
-			if (n.size() > 4 && n.substr(n.size() - 4) == ".png") out.push_back(dir + "/" + n);
-		}
-		closedir(d);
-	}
-	sort(out.begin(), out.end());
-	return out;
-}
-
-// kernel.cpp:51-58: drop the 5 leading digits of the file name, parse the rest; the lambda returns float
-static double stamp_of(const string &fn) {
-	const size_t s = fn.find_last_of("/");
-	return (float)stod(fn.substr(s + 6, fn.find_last_of(".") - s - 6));
-}
+#include "tum_io.hpp"
 
 int main(int argc, char **argv) {
 	string root = ".", render = "render.ppm", render_color, ply;
@@ -157,7 +54,7 @@ int main(int argc, char **argv) {
 		else root = a;
 	}
 	try {
-		auto tsdf = make_shared<TSDF>(intr, dim, bins);
+		shared_ptr<TSDF> tsdf;  // created from the first decoded frame's size
 		auto traj = read_trajactory(root + "/groundtruth.txt");
 		vector<string> rgb_fn = glob_png(root + "/rgb"), depth_fn = glob_png(root + "/depth"), mask_fn = glob_png(root + "/mask");
 		if (traj.empty() || depth_fn.empty() || mask_fn.empty() || rgb_fn.size() != mask_fn.size()) {
@@ -167,26 +64,78 @@ int main(int argc, char **argv) {
 		vector<double> depth_ts, mask_ts;
 		for (auto &f : depth_fn) depth_ts.push_back(stamp_of(f));
 		for (auto &f : mask_fn) mask_ts.push_back(stamp_of(f));
+		// association pass (kernel.cpp:64-74): which depth frame goes with which mask / rgb frame
+		vector<pair<size_t, size_t>> pairs;
 		size_t j = 0;
-		unique_ptr<Viewer> viewer;
-		int cnt = 0;
-		for (size_t i = 0; i < depth_ts.size(); i++) {  // kernel.cpp:64-100
+		for (size_t i = 0; i < depth_ts.size(); i++) {
 			if (depth_ts[i] < begin || depth_ts[i] > end) continue;
 			while (i < depth_ts.size() && j < mask_ts.size() && depth_ts[i] < mask_ts[j]) i++;
 			while (i < depth_ts.size() && j < mask_ts.size() && mask_ts[j] < depth_ts[i]) j++;
 			if (i >= depth_ts.size() || j >= mask_ts.size()) break;  // (the reference runs off the end here, kernel.cpp:67)
-			sfm::Mat depth_img, mask_img, rgb_img;
-			if (!read_png(depth_fn[i], depth_img, false) || !read_png(mask_fn[j], mask_img, false) || !read_png(rgb_fn[j], rgb_img, true)) {
-				cerr << "cannot decode " << depth_fn[i] << " / " << mask_fn[j] << " / " << rgb_fn[j] << endl;
+			if ((int)pairs.size() >= max_frames) break;            // kernel.cpp:73-74
+			pairs.push_back(make_pair(i, j));
+		}
+		// decode thread: keeps up to kAhead decoded frames ready
+		struct Decoded { sfm::Mat depth, mask, rgb; bool ok = false; };
+		const size_t kAhead = 3;
+		vector<Decoded> ring(kAhead);
+		mutex mu;
+		condition_variable cv_full, cv_free;
+		size_t produced = 0, consumed = 0;
+		bool stop = false;
+		thread decoder([&]() {
+			for (size_t k = 0; k < pairs.size(); k++) {
+				{
+					unique_lock<mutex> lk(mu);
+					cv_free.wait(lk, [&] { return stop || produced - consumed < kAhead; });
+					if (stop) return;
+				}
+				Decoded d;
+				d.ok = read_png(depth_fn[pairs[k].first], d.depth, false) && read_png(mask_fn[pairs[k].second], d.mask, false) &&
+					read_png(rgb_fn[pairs[k].second], d.rgb, true);
+				{
+					lock_guard<mutex> lk(mu);
+					ring[k % kAhead] = std::move(d);
+					produced++;
+				}
+				cv_full.notify_one();
+			}
+		});
+		struct Joiner { thread &t; mutex &m; bool &stop; condition_variable &cv; ~Joiner() { { lock_guard<mutex> lk(m); stop = true; } cv.notify_all(); if (t.joinable()) t.join(); } } joiner{decoder, mu, stop, cv_free};
+		unique_ptr<Viewer> viewer;
+		int width = 0, height = 0;
+		const auto t_start = chrono::steady_clock::now();
+		for (size_t k = 0; k < pairs.size(); k++) {
+			const size_t i = pairs[k].first, jj = pairs[k].second;
+			Decoded d;
+			{
+				unique_lock<mutex> lk(mu);
+				cv_full.wait(lk, [&] { return produced > k; });
+				d = std::move(ring[k % kAhead]);
+				consumed++;
+			}
+			cv_free.notify_one();
+			sfm::Mat &depth_img = d.depth, &mask_img = d.mask, &rgb_img = d.rgb;
+			if (!d.ok) {
+				cerr << "cannot decode " << depth_fn[i] << " / " << mask_fn[jj] << " / " << rgb_fn[jj] << endl;
 				return 2;
 			}
 			if (depth_img.elem_bytes != 2 || depth_img.channels != 1 || rgb_img.channels != 3 || mask_img.channels != 1) {
 				cerr << "unexpected pixel formats (need 16-bit depth, 8-bit RGB, 8-bit labels)" << endl;
 				return 2;
 			}
-			cout << "processing: " << i << ", " << rgb_fn[j] << endl;
-			if (++cnt > max_frames) break;  // kernel.cpp:73-74
-			if (!viewer) viewer.reset(new Viewer(depth_img.cols, depth_img.rows));
+			cout << "processing: " << i << ", " << rgb_fn[jj] << endl;
+			if (!tsdf) {  // the reference sizes everything from the first depth frame (tsdf.cu:225, kernel.cpp:76-78)
+				width = depth_img.cols;
+				height = depth_img.rows;
+				tsdf = make_shared<TSDF>(intr, dim, bins, width, height);
+				viewer.reset(new Viewer(width, height));
+			}
+			if (depth_img.cols != width || depth_img.rows != height || rgb_img.cols != width || rgb_img.rows != height ||
+				mask_img.cols != width || mask_img.rows != height) {
+				cerr << "frame " << depth_fn[i] << ": image size differs from the first frame's " << width << "x" << height << endl;
+				return 2;
+			}
 			const float mean = sfm_mean_depth((const uint16_t *)depth_img.data, depth_img.rows * depth_img.cols);  // kernel.cpp:95
 			auto low = traj.lower_bound(depth_ts[i]);  // kernel.cpp:97 (no interpolation)
 			if (low == traj.end()) --low;
@@ -196,13 +145,21 @@ int main(int argc, char **argv) {
 				// that bracket the depth timestamp instead of taking the next one
 				auto prev = std::prev(low);
 				double a8[8] = {prev->first}, b8[8] = {low->first}, pose7[7];
-				for (int k = 0; k < 7; k++) { a8[1 + k] = prev->second[k]; b8[1 + k] = low->second[k]; }
+				for (int q = 0; q < 7; q++) { a8[1 + q] = prev->second[q]; b8[1 + q] = low->second[q]; }
 				sfm_interpolate_pose(a8, b8, depth_ts[i], pose7);
 				sfm_parse_extrinsic(pose7, extrinsic);
 			} else
 				sfm_parse_extrinsic(low->second.data(), extrinsic);  // kernel.cpp:98
 			tsdf->parse_frame(depth_img, rgb_img, mask_img, extrinsic, mean);  // kernel.cpp:99
 		}
+		if (!tsdf) {
+			cerr << "no frame inside the time window" << endl;
+			return 2;
+		}
+		sfm_synchronize(tsdf->handle());
+		const double secs = chrono::duration<double>(chrono::steady_clock::now() - t_start).count();
+		cout << "frames from disk: " << pairs.size() << " in " << secs << " s = " << (pairs.size() / max(secs, 1e-9))
+		     << " frames/s (PNG decode on a second thread, " << kAhead << " frames ahead)" << endl;
 		const sfm_info info = tsdf->info();
 		cout << "fused " << info.n_obs << " frames, num_objs " << info.num_objs << ", voxel " << info.voxel[0] << " m" << endl;
 		if (viewer) {  // kernel.cpp:101-107 spins forever; we render `views` steps and keep the last image

@@ -318,6 +318,11 @@ int sfm_stats_end(sfm_volume *v, uint64_t ticket, uint64_t *U_total, uint64_t *S
 int sfm_debug_divcheck(float b, unsigned seed, int blocks, int per_thread, float amax, uint64_t *mismatches);
 
 /* Host-side helpers of the reference's driver (the "next" rows). */
+/* extrinsic.inv() (tsdf.cu:177) and extrinsic * init_extrinsic_inv (tsdf.cu:217) exactly as sfm_parse_frame computes
+ * them (float inputs, double accumulation): for callers that shard the volume themselves (driver/kernel_mgpu.cpp). */
+int sfm_mat4_inv(const float *m16, float *out16);
+void sfm_mat4_mul(const float *a16, const float *b16, float *out16);
+
 /* mean_depth (utils.cu:77-91). */
 float sfm_mean_depth(const uint16_t *depth, int n);
 /* parse_extrinsic (utils.cu:8-24): pose {tx,ty,tz,qx,qy,qz,qw} -> world->camera 4x4 f32. */

@@ -74,6 +74,8 @@ SYMBOLS = {
     "sfm_merge_decide": (_i, [_vp, _vp, _vp, _vp, C.POINTER(MergeReport)]),
     "sfm_last_merge": (_i, [_vp, C.POINTER(MergeReport)]),
     "sfm_set_num_objs": (_i, [_vp, _i]),
+    "sfm_mat4_inv": (_i, [_vp, _vp]),
+    "sfm_mat4_mul": (None, [_vp, _vp, _vp]),
     "sfm_download": (_i, [_vp, _i, _vp, _sz]),
     "sfm_upload": (_i, [_vp, _i, _vp, _sz]),
     "sfm_plane_bytes": (_sz, [_vp, _i]),

@@ -1854,6 +1854,15 @@ int sfm_debug_divcheck(float b, unsigned seed, int blocks, int per_thread, float
 	return SFM_OK;
 }
 
+/* The two small host products parse_frame is built from (tsdf.cu:177 extrinsic.inv(), tsdf.cu:217 extrinsic *
+ * init_extrinsic_inv): exported so that a caller that shards the volume itself (driver/kernel_mgpu.cpp) feeds every
+ * slab the same extrinsic2init bits the single-volume sfm_parse_frame computes. */
+int sfm_mat4_inv(const float *m16, float *out16) {
+	if (!m16 || !out16) return fail(SFM_ERR_INVALID, "null argument");
+	return mat4_inv(m16, out16) ? SFM_OK : fail(SFM_ERR_INVALID, "singular matrix");
+}
+void sfm_mat4_mul(const float *a16, const float *b16, float *out16) { mat4_mul(a16, b16, out16); }
+
 float sfm_mean_depth(const uint16_t *depth, int n) {  // utils.cu:77-91
 	double sum = 0;
 	int total = 0;

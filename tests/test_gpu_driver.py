@@ -101,3 +101,34 @@ def test_cpp_driver_colour_view_ply_and_interpolated_poses(tmp_path):
     assert r2.returncode == 0, r2.stdout
     n2 = int(re.search(r"surface: (\d+) points", r2.stdout).group(1))
     assert abs(n2 - n_pts) <= 0.05 * n_pts
+
+
+def _ppm(path):
+    data = open(path, "rb").read()
+    return np.frombuffer(data[data.index(b"255\n") + 4:], np.uint8)
+
+
+@pytest.mark.parametrize("ngpu", [1, 2])
+def test_cpp_multi_gpu_driver_matches_single_volume_driver(tmp_path, ngpu):
+    """driver/sfm_driver_mgpu (z-slabs, NCCL called directly from C++: frame broadcast, three MIN all-reduces and two SUM
+    all-reduces per merged frame, all-gather of the SDF and of the hits + one MIN all-reduce per view) against
+    driver/sfm_driver (one whole volume) on the same sequence: frame count, num_objs and the rendered image are equal."""
+    import torch
+    drv, drv_m = os.path.join(ROOT, "driver", "sfm_driver"), os.path.join(ROOT, "driver", "sfm_driver_mgpu")
+    if not (os.path.exists(drv) and os.path.exists(drv_m)):
+        pytest.skip("drivers not built")
+    if torch.cuda.device_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    seq = str(tmp_path / "seq")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_sequence.py"), seq, "7", "4"], check=True)
+    a, b = str(tmp_path / "one.ppm"), str(tmp_path / "many.ppm")
+    common = [seq, "--dim", "128", "--bins", "32", "--views", "3"]
+    r1 = subprocess.run([drv] + common + ["--render", a], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    r2 = subprocess.run([drv_m] + common + ["--render", b, "--gpus", str(ngpu)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r1.returncode == 0, r1.stdout
+    assert r2.returncode == 0, r2.stdout
+    m1 = re.search(r"fused (\d+) frames, num_objs (\d+)", r1.stdout)
+    m2 = re.search(r"fused (\d+) frames, num_objs (\d+)", r2.stdout)
+    assert m1 and m2 and m1.groups() == m2.groups(), (r1.stdout[-300:], r2.stdout[-300:])
+    assert int(re.search(r"\((\d+) labelled pixels\)", r2.stdout).group(1)) > 1000
+    assert (_ppm(a) == _ppm(b)).all(), "multi-GPU driver and single-volume driver must render the same image"
