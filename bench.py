@@ -486,6 +486,10 @@ def run_ours(args):
     # all of its colour/histogram updates), so the slab boundaries follow a per-plane cost profile measured
     # on the GPU from the first frames at full z resolution (128 x 128 x Dz pre-pass, one histogram bin)
     from slam_maskrcnn_b200 import slabs as slabs_mod
+    # N > 1: every slab stores 4 planes beyond its owned range on the high-z side (integrated redundantly, never
+    # exchanged): the ray-cast labels a hit from the planes z and z + 1 of the rank that owns z.  (The exact
+    # three-stage paths need ceil(vx / vz) + 2 planes on both sides; the parity side volume has them.)
+    halo = 4 if world > 1 else 0
     profile = None
     if world > 1 and not args.equal_slabs:
         def profile_volume(pdims):
@@ -496,20 +500,17 @@ def run_ours(args):
             pv.set_bounds(s_, e_, vox, place[3])
             return pv
         profile, _, _ = slabs_mod.work_profile_z(profile_volume, frames[:3], dims)
-        plan = slabs_mod.plan_slabs(dims[2], world, profile)
+        plan = slabs_mod.plan_slabs(dims[2], world, profile, halo_hi=halo)
     else:
         plan = slabs_mod.plan_slabs(dims[2], world)
     from slam_maskrcnn_b200 import synth as synth_mod
     md0 = synth_mod.mean_depth(sc.frame(0)["depth"])
-    halo = slabs_mod.shard_halo(place[2]) if world > 1 else 0
 
     def make_volume(plan):
         # FLAG_ASYNC_SOURCES: every frame of the pool has its own pinned buffer that is never rewritten, so the
         # host-buffer call may return before its H2D copy has finished (sfm_b200.h, "Buffer lifetime")
         from slam_maskrcnn_b200 import FLAG_ASYNC_SOURCES
-        # N > 1: the slab is stored with the halo the sharded ray-cast needs (a few planes on both sides of the owned
-        # range, integrated redundantly, never exchanged)
-        stored = slabs_mod.stored_range(plan[rank][0], plan[rank][1], dims[2], halo, align=8) if world > 1 else plan[rank]
+        stored = (plan[rank][0], min(dims[2] - plan[rank][0], plan[rank][1] + halo)) if world > 1 else plan[rank]
         v = Volume(dims=dims, bins=bins, width=640, height=480, K=K, Kinv=Kinv, device=local, slab=stored, own=plan[rank],
                    flags=args.flags | FLAG_ASYNC_SOURCES)
         v.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -617,7 +618,7 @@ def run_ours(args):
             ts = [float(t.item()) for t in ts]
             calib.append([round(t, 4) for t in ts])
             profile = slabs_mod.refine_profile(profile, plan, ts)
-            new_plan = slabs_mod.plan_slabs(dims[2], world, profile)
+            new_plan = slabs_mod.plan_slabs(dims[2], world, profile, halo_hi=halo)
             if new_plan == plan:
                 break
             plan = new_plan
@@ -851,7 +852,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, dims), "dims": list(dims), "bins": bins,
                        "voxels_per_gpu": [dims[0] * dims[1] * p[1] for p in plan], "z_slabs": [list(p) for p in plan],
-                       "halo_planes_per_side": halo,
+                       "halo_planes_high_side": halo,
                        "slab_plan": "equal thickness" if (world == 1 or args.equal_slabs) else "boundaries from a per-plane GPU cost profile of the first 3 frames (128x128xDz pre-pass: touched and near-surface voxels per plane), rescaled per slab from measured kernel times in an untimed calibration pass; slabs <= 3x the mean thickness",
                        "slab_calibration_ms": calib,
                        "frame_pool": n_pool,

@@ -77,17 +77,22 @@ def work_profile_z(volume_factory, frames, dims, coarse_xy=128):
     return cost / cost.sum(), u, s_
 
 
-def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
+def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0, halo_hi=0):
     """Contiguous z-slabs [(z0, nz)] for `world` ranks.  Without a profile: equal thickness.  With a
     per-plane cost profile: the partition minimising the largest slab cost subject to every slab being
     a multiple of `align` planes and at most max_factor * dz / world planes thick (memory: the
-    histogram of a slab must fit one GPU).  Greedy sweep inside a bisection on the cost bound."""
+    histogram of a slab must fit one GPU).  Greedy sweep inside a bisection on the cost bound.
+    `halo_hi`: planes every slab stores (and integrates) beyond its owned range on the high-z side; their cost is
+    charged to the slab (a fraction halo_hi / align of the next chunk), which matters for the thin slabs a
+    fronto-parallel wall ends up in."""
     if profile is None or world == 1:
         return [slab_range(r, world, dz, align=min(align, 4)) for r in range(world)]
     assert len(profile) == dz and dz % align == 0 and dz // align >= world
     cost = np.asarray(profile, np.float64).reshape(dz // align, align).sum(1)
     cost = cost / cost.sum()
     nchunks = len(cost)
+    hfrac = min(1.0, halo_hi / float(align))
+    halo_cost = np.append(cost[1:], 0.0) * hfrac  # halo_cost[i] = what a slab ENDING with chunk i pays for its halo
     max_c = max(1, int(max_factor * dz / world) // align)
     assert max_c * world >= nchunks, "max_factor too small to cover the volume"
 
@@ -98,7 +103,7 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
             remaining_slabs = world - r - 1
             # leave >= 1 chunk per later slab, and no more than the later slabs can hold
             while i < nchunks and n < max_c and nchunks - i > remaining_slabs:
-                if n > 0 and acc + cost[i] > bound and (nchunks - i) <= remaining_slabs * max_c:
+                if n > 0 and acc + cost[i] + halo_cost[i] > bound and (nchunks - i) <= remaining_slabs * max_c:
                     break
                 acc += cost[i]
                 i += 1
@@ -107,7 +112,7 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
         return cuts if i == nchunks else None
 
     def worst(cuts):
-        return max(cost[cuts[r]:cuts[r + 1]].sum() for r in range(world))
+        return max(cost[cuts[r]:cuts[r + 1]].sum() + halo_cost[cuts[r + 1] - 1] for r in range(world))
 
     lo, hi = 1.0 / world, 1.0
     best = sweep(hi)
@@ -126,7 +131,7 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
     def feasible(i, slabs_left):
         for _ in range(slabs_left):
             acc, n = 0.0, 0
-            while i < nchunks and n < max_c and (n == 0 or acc + cost[i] <= cap):
+            while i < nchunks and n < max_c and (n == 0 or acc + cost[i] + halo_cost[i] <= cap):
                 acc += cost[i]
                 i += 1
                 n += 1
@@ -139,7 +144,7 @@ def plan_slabs(dz, world, profile=None, align=8, max_factor=3.0):
         acc, n = 0.0, 0
         while i + n < nchunks - left and n < max_c:
             c = cost[i + n]
-            if n > 0 and acc + c > cap:
+            if n > 0 and acc + c + halo_cost[i + n] > cap:
                 break
             if n > 0 and acc + 0.5 * c > desired and feasible(i + n, left):
                 break
