@@ -570,9 +570,16 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		return i < nmixed ? wl.mixed[i] : wl.free_[i - nmixed];
 #endif
 	};
-	auto fetch = [&]() {  // lane 0 holds the result; broadcast when it is needed
+	// lane 0 holds the result; it is broadcast when the group is needed, one group of bricks later.  Around an atomic add
+	// on a warp-uniform address ptxas builds its warp-aggregation idiom (leader election, ATOMG, shuffle of the result to
+	// the participants) even when one lane takes part, and that shuffle waits for the atomic's round trip on the spot:
+	// 11 % of K1b's stall samples.  `opaque0` is 0 at run time but not provably uniform, which keeps the plain ATOMG.
+	unsigned opaque0;
+	asm("{\n\t.reg .u32 a, b;\n\tmov.u32 a, %%laneid;\n\tmov.u32 b, %%smid;\n\tadd.u32 a, a, b;\n\tshr.u32 %0, a, 24;\n\t}" : "=r"(opaque0));
+	unsigned *const cursor = wl.counts + 2 + opaque0;
+	auto fetch = [&]() {
 		unsigned b = 0;
-		if (lane == 0) b = atomicAdd(wl.counts + 2, (unsigned)kFetch);
+		if (lane == 0) b = atomicAdd(cursor, (unsigned)kFetch);
 		return b;
 	};
 	// prefetch.global.L2 of the SDF / weight lines of bricks 1.. of a freshly fetched group (brick 0 is
