@@ -32,10 +32,26 @@ def make_slabs(sc, world, plan=None):
     (4, (64, 64, 96), 32, 6, [(0, 40), (40, 16), (56, 8), (64, 32)]),  # uneven, thin slabs around the surfaces
 ])
 def test_sharded_merge_equals_single_volume(world, dims, bins, ninst, plan):
-    import torch
     sc = Scenario(dims=dims, bins=bins, n_instances=ninst, frames=6, yaw_step_deg=2.0, permute=True)
     full = sc.make_volume()
     slabs = make_slabs(sc, world, plan)
+    assert fuse_whole_and_sharded(sc, full, slabs) == len(sc.frames) - 1
+    ref = {k: full.download(k) for k in ("sdf", "weight", "color", "hist")}
+    assert ref["hist"].sum() > 0
+    for v, sz0, snz in slabs:
+        assert v.info().num_objs == full.info().num_objs
+        for k in ref:
+            got, want = v.download(k), np.ascontiguousarray(ref[k][:, :, sz0:sz0 + snz])
+            same = (bits(got) == bits(want)) if k == "sdf" else (got == want)
+            assert same.all(), f"slab [{sz0},{sz0 + snz}) plane {k} differs after the sharded merge"
+        v.close()
+    full.close()
+
+
+def fuse_whole_and_sharded(sc, full, slabs):
+    """Every frame of `sc` through sfm_fuse_frame on `full` and through the sharded sequence on `slabs` (emulated ranks);
+    asserts equal relabelled masks and merge reports frame by frame; returns the number of merged frames."""
+    import torch
     n = sc.W * sc.H
     n64, ntot = full.fold_table_bytes()
     merged_frames = 0
@@ -88,14 +104,4 @@ def test_sharded_merge_equals_single_volume(world, dims, bins, ninst, plan):
         for (v, *_), dm in zip(slabs, d_masks):
             v.integrate_dev(d_depth.data_ptr(), d_color.data_ptr(), dm.data_ptr(), E)
             v.synchronize()
-    assert merged_frames == len(sc.frames) - 1
-    ref = {k: full.download(k) for k in ("sdf", "weight", "color", "hist")}
-    assert ref["hist"].sum() > 0
-    for v, sz0, snz in slabs:
-        assert v.info().num_objs == full.info().num_objs
-        for k in ref:
-            got, want = v.download(k), np.ascontiguousarray(ref[k][:, :, sz0:sz0 + snz])
-            same = (bits(got) == bits(want)) if k == "sdf" else (got == want)
-            assert same.all(), f"slab [{sz0},{sz0 + snz}) plane {k} differs after the sharded merge"
-        v.close()
-    full.close()
+    return merged_frames
