@@ -24,10 +24,15 @@ driver/sfm_driver_mgpu: driver/kernel_mgpu.cpp driver/tum_io.hpp include/sfm_b20
 	g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include -o $@ driver/kernel_mgpu.cpp -L$(PKG) -lsfm_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' \
 		-L/usr/local/cuda/lib64 -lcudart -lnccl -lz
 
+# A/B build of K1b with cp.async.bulk.tensor.2d depth tiles (measured slower, profiles/r2_k1_tma_tensor_ab.txt);
+# select it with SFM_B200_LIB=$PWD/build/lib_tma.so
+ab_tma:
+	mkdir -p build && $(NVCC) $(NVFLAGS) -DSFM_K1_TMA_DEPTH=1 -shared -o build/lib_tma.so $(CSRC)
+
 ref:
 	python oracle/build_ref.py
 
 clean:
 	rm -f $(LIB) oracle/liboracle.so driver/sfm_driver driver/sfm_driver_mgpu
 
-.PHONY: all ref clean
+.PHONY: all ref clean ab_tma

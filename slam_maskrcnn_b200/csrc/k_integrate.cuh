@@ -218,6 +218,7 @@ __device__ __forceinline__ void red_add_hint(uint32_t *a, unsigned inc, unsigned
 	asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(inc), "l"(pol) : "memory");
 }
 
+constexpr int kTmaBoxW = 32, kTmaBoxH = 16;  // SFM_K1_TMA_DEPTH build: pixels of depth_m staged per brick
 constexpr int kQueue = 160;  // per-warp capacity of the deferred near-surface queue (one brick = 128 voxels, drained at >= 32)
 
 // Colour running mean + histogram increment (tsdf.cu:57-62) for the queued near-surface voxels, one
@@ -516,7 +517,11 @@ __global__ void __launch_bounds__(kK1aThreads) classify_kernel(VolGeom g, FrameV
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool LABELS, bool KCANON>
 __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_kernel(Planes p, VolGeom g, FrameView f, WorkLists wl,
-	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err, const int32_t *__restrict__ gate)
+	unsigned long long *__restrict__ stats, uint32_t *__restrict__ err, const int32_t *__restrict__ gate
+#if SFM_K1_TMA_DEPTH
+	, const __grid_constant__ CUtensorMap depth_tmap
+#endif
+	)
 {
 	// `gate` (nullable): a device flag set by an earlier kernel of the same frame (the merge decision overflowed the
 	// histogram's bins): the frame must then leave the volume untouched
@@ -533,6 +538,19 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 	extern __shared__ __align__(128) unsigned char smem_dyn[];
 	uint4 *q = reinterpret_cast<uint4 *>(smem_dyn) + warp * kQueue;
 	int qcount = 0;  // warp-uniform
+#if SFM_K1_TMA_DEPTH
+	// A/B build: per warp a kTmaBoxH x kTmaBoxW f32 tile of depth_m, filled by cp.async.bulk.tensor.2d (SASS: UTMALDG)
+	// at the top-left corner of the brick's pixel footprint, completion on a per-warp mbarrier
+	float *tile = reinterpret_cast<float *>(smem_dyn + (kK1Threads / 32) * kQueue * sizeof(uint4)) + warp * (kTmaBoxW * kTmaBoxH);
+	const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(smem_dyn + (kK1Threads / 32) * (kQueue * sizeof(uint4) + kTmaBoxW * kTmaBoxH * 4) + warp * 8);
+	unsigned tma_parity = 0;
+	if (lane == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+#endif
 	const unsigned nmixed = wl.counts[0], total = nmixed + wl.counts[1];
 	auto brick_coords = [&](unsigned id, int &x, int &y, int &zl) {  // warp-uniform id + lane offsets
 		x = (int)(id >> kIdXShift);
@@ -653,6 +671,9 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 		// carries no per-voxel branches.
 		float czv[VEC], diffv[VEC], sxv[VEC], syv[VEC], szv[VEC];
 		int img[VEC];
+#if SFM_K1_TMA_DEPTH
+		int ixv[VEC], iyv[VEC];
+#endif
 		unsigned inb = 0, inexact = 0;
 		// phase 1: projection -> pixel (no memory).  tsdf.cu:30-46
 #pragma unroll
@@ -672,6 +693,9 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 			const int ix = __float2int_rd(qx), iy = __float2int_rd(qy);
 			if ((unsigned)ix < (unsigned)f.W && (unsigned)iy < (unsigned)f.H) inb |= 1u << k;
 			img[k] = iy * f.W + ix;
+#if SFM_K1_TMA_DEPTH
+			ixv[k] = ix; iyv[k] = iy;
+#endif
 		}
 		if (inexact) {  // ~1 voxel in 10^4: decide with the exact IEEE divides (out-of-line helper)
 #pragma unroll
@@ -681,13 +705,52 @@ __global__ void __launch_bounds__(SFM_K1_THREADS, SFM_K1_MIN_BLOCKS) integrate_k
 					const bool in = (unsigned)ix < (unsigned)f.W && (unsigned)iy < (unsigned)f.H;
 					inb = (inb & ~(1u << k)) | ((in ? 1u : 0u) << k);
 					img[k] = iy * f.W + ix;
+#if SFM_K1_TMA_DEPTH
+					ixv[k] = ix; iyv[k] = iy;
+#endif
 				}
 		}
 		if (!ok) inb = 0;
 		// phase 2: depth (metres, = depth/5000.f computed once per pixel by K0), all VEC loads at once
 		float dm[VEC];
+#if SFM_K1_TMA_DEPTH
+		{
+			int lx = 0x7fffffff, ly = 0x7fffffff;
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				if ((inb >> k) & 1u) { lx = min(lx, ixv[k]); ly = min(ly, iyv[k]); }
+			// the box must start on a 16-byte boundary of the innermost dimension (an odd start raises 'illegal instruction')
+			const int xr = __reduce_min_sync(0xffffffffu, lx), x0 = xr & ~3, y0 = __reduce_min_sync(0xffffffffu, ly);
+			if (xr != 0x7fffffff) {  // warp-uniform: some voxel of the brick projects into the image
+				__syncwarp();  // every lane is done with the previous tile
+				if (lane == 0) {
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(kTmaBoxW * kTmaBoxH * 4) : "memory");
+					asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+						::"r"(tile_s), "l"(reinterpret_cast<unsigned long long>(&depth_tmap)), "r"(bar_s), "r"(x0), "r"(y0) : "memory");
+				}
+				unsigned done = 0;
+				while (!done)
+					asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						: "=r"(done) : "r"(bar_s), "r"(tma_parity) : "memory");
+				tma_parity ^= 1u;
+			}
+#pragma unroll
+			for (int k = 0; k < VEC; k++) {
+				const int rx = ixv[k] - x0, ry = iyv[k] - y0;
+				const bool in = (inb >> k) & 1u;
+				if (in && (unsigned)rx < (unsigned)kTmaBoxW && (unsigned)ry < (unsigned)kTmaBoxH) {
+					dm[k] = tile[ry * kTmaBoxW + rx];
+					if (f.debug & 64) atomicAdd(err + 2, 1u);  // coverage counter of the A/B
+				} else {
+					dm[k] = __ldg(f.depth_m + (in ? img[k] : 0));
+					if ((f.debug & 64) && in) atomicAdd(err + 3, 1u);
+				}
+			}
+		}
+#else
 #pragma unroll
 		for (int k = 0; k < VEC; k++) dm[k] = __ldg(f.depth_m + (((inb >> k) & 1u) ? img[k] : 0));
+#endif
 		// phase 3: tsdf.cu:48-52
 		float nd[VEC];
 		unsigned touched = 0, band = 0, surface = 0;

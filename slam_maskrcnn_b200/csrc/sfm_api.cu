@@ -115,6 +115,7 @@ struct sfm_volume {
 	struct PrepCtx {
 		uint16_t *d_tilemax = nullptr, *d_tilemin = nullptr;  // one allocation: [tilemax | tilemin], padded to 16 B
 		float *d_depth_m = nullptr;
+		alignas(64) unsigned char depth_tmap[128] = {};  // SFM_K1_TMA_DEPTH build: CUtensorMap of d_depth_m
 		unsigned *d_work = nullptr;                  // WorkLists::counts (3 counters, zeroed by K0)
 		uint32_t *d_list_mixed = nullptr, *d_list_free = nullptr;  // K1a -> K1b brick lists, one slot per brick each
 		cudaEvent_t ev_ready = nullptr;  // K1a of the frame that uses this context is done (prep_stream)
@@ -294,6 +295,9 @@ FrameView make_frame_view(const sfm_volume *v, const sfm_volume::PrepCtx &c, con
 	f.tilemin = c.d_tilemin;
 	f.tile_bytes = (unsigned)v->tile_bytes;
 	f.depth_m = c.d_depth_m;
+#if SFM_K1_TMA_DEPTH
+	f.depth_tmap = c.depth_tmap;
+#endif
 	f.W = v->W; f.H = v->H; f.TW = v->TW; f.TH = v->TH;
 	memcpy(f.E, E16, 12 * sizeof(float));
 	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) f.K[r * 3 + c] = v->K[r * 4 + c];
@@ -361,7 +365,7 @@ void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl, cons
 	// persistent grid: one resident wave (occupancy x SM count); the warps pull bricks from the lists.
 	// dynamic shared memory: the per-warp surface queues
 	constexpr int warps = kK1Threads / 32;
-	const size_t smem = warps * kQueue * sizeof(uint4);
+	const size_t smem = warps * (kQueue * sizeof(uint4) + (SFM_K1_TMA_DEPTH ? kTmaBoxW * kTmaBoxH * 4 + 8 : 0));
 	int &per_sm = v->k1b_per_sm[(VEC == 4 ? 4 : 0) + (LABELS ? 2 : 0) + (KCANON ? 1 : 0)];
 	auto kern = integrate_kernel<VEC, LABELS, KCANON>;
 	if (!per_sm) {
@@ -381,7 +385,11 @@ void launch_update2(sfm_volume *v, const FrameView &f, const WorkLists &wl, cons
 	}
 	const long long want = ((long long)v->nbricks + warps - 1) / warps;
 	const int blocks = (int)std::max(1LL, std::min<long long>((long long)per_sm * v->num_sms, want));  // persistent: one resident wave
+#if SFM_K1_TMA_DEPTH
+	kern<<<blocks, kK1Threads, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err, gate, *(const CUtensorMap *)f.depth_tmap);
+#else
 	kern<<<blocks, kK1Threads, smem, v->stream>>>(v->planes, v->g, f, wl, v->d_stats, v->d_err, gate);
+#endif
 }
 
 template <int VEC, bool LABELS>
@@ -890,7 +898,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	sfm_volume *v = new sfm_volume();
 	v->desc = *desc;
 	if (desc->flags & SFM_FLAG_DEBUG_ABLATE) {  // profiling only: a stray environment variable alone changes nothing
-		if (const char *e = getenv("SFM_DEBUG_ABLATE")) v->debug_ablate = atoi(e) & ~64;
+		if (const char *e = getenv("SFM_DEBUG_ABLATE")) v->debug_ablate = atoi(e) & ~(SFM_K1_TMA_DEPTH ? 0 : 64);
 	}
 	v->bins = desc->bins;
 	v->W = desc->width;
@@ -978,6 +986,25 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		CU_OR_DESTROY(cudaMemset(c.d_tilemax, 0, v->tile_bytes));
 		c.d_tilemin = c.d_tilemax + (size_t)v->TW * v->TH;
 		CU_OR_DESTROY(cudaMalloc(&c.d_depth_m, npx * 4));
+#if SFM_K1_TMA_DEPTH
+		{
+			typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+				const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+			void *fn = nullptr;
+			cudaDriverEntryPointQueryResult qr;
+			CU_OR_DESTROY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+			alignas(64) CUtensorMap tm;
+			const cuuint64_t gdim[2] = {(cuuint64_t)v->W, (cuuint64_t)v->H}, gstride[1] = {(cuuint64_t)v->W * 4};
+			const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)kTmaBoxH}, estr[2] = {1, 1};
+			if (!fn || ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.d_depth_m, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+					CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+				sfm_destroy(v);
+				return fail(SFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+			}
+			static_assert(sizeof(tm) == sizeof(c.depth_tmap), "CUtensorMap is 128 bytes");
+			memcpy(c.depth_tmap, &tm, sizeof(tm));
+		}
+#endif
 		CU_OR_DESTROY(cudaMalloc(&c.d_work, 32));
 		CU_OR_DESTROY(cudaMemset(c.d_work, 0, 32));
 		CU_OR_DESTROY(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
@@ -987,7 +1014,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_ray_stats, 16));
 	CU_OR_DESTROY(cudaMemset(v->d_ray_stats, 0, 16));
-	CU_OR_DESTROY(cudaMalloc(&v->d_err, 4));
+	CU_OR_DESTROY(cudaMalloc(&v->d_err, 16));
 	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
 		// brick shape on the 128-bit path: 32 planes per brick unless the slab is so thin that more than half the lanes
 		// of such a brick would fall outside it (see VolGeom::zl_log2); SFM_ZL_LOG2 overrides (experiments)
@@ -1019,7 +1046,7 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 		}
 	}
 	v->num_sms = prop.multiProcessorCount;
-	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 4));
+	CU_OR_DESTROY(cudaMemset(v->d_err, 0, 16));
 	CU_OR_DESTROY(cudaMalloc(&v->d_palette, 256 * 3));
 	CU_OR_DESTROY(cudaMalloc(&v->d_lut, 256));
 	{
@@ -1072,6 +1099,13 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->ev_call) cudaEventDestroy(v->ev_call);
 	cudaFree(v->d_stats);
 	cudaFree(v->d_ray_stats);
+#if SFM_K1_TMA_DEPTH
+	if (v->debug_ablate & 64) {
+		uint32_t e[4] = {0, 0, 0, 0};
+		if (v->d_err && cudaMemcpy(e, v->d_err, 16, cudaMemcpyDeviceToHost) == cudaSuccess)
+			fprintf(stderr, "[sfm A/B] depth reads served by the TMA tile: %u, by the LDG fallback: %u\n", e[2], e[3]);
+	}
+#endif
 	cudaFree(v->d_err); cudaFree(v->d_palette); cudaFree(v->d_lut);
 	cudaFree(v->d_probs); cudaFree(v->d_box); cudaFree(v->d_t); cudaFree(v->d_flags); cudaFree(v->d_bgr);
 	cudaFree(v->d_label); cudaFree(v->d_keys); cudaFree(v->d_hits); cudaFree(v->d_fold);

@@ -7,6 +7,9 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#if defined(SFM_K1_TMA_DEPTH) && SFM_K1_TMA_DEPTH
+#include <cuda.h>  // CUtensorMap (A/B build only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+#endif
 
 namespace sfm {
 
@@ -65,6 +68,9 @@ struct Planes {
 	unsigned occ2_off;
 };
 
+#ifndef SFM_K1_TMA_DEPTH
+#define SFM_K1_TMA_DEPTH 0  // 1: A/B build that stages K1b's depth gathers with cp.async.bulk.tensor.2d (profiles/README.md)
+#endif
 struct FrameView {
 	const uint16_t *depth;
 	const uint8_t *rgb;
@@ -83,6 +89,9 @@ struct FrameView {
 	float cull_k2;      // |K20|+|K21|+|K22|
 	float cull_slack0;  // constant pixel slack
 	int debug;          // ablation switches for profiling (0 in production)
+#if SFM_K1_TMA_DEPTH
+	const void *depth_tmap;  // host pointer to the CUtensorMap of depth_m (A/B build only; passed to K1b as a __grid_constant__ parameter)
+#endif
 };
 
 // dot(float4 row,(p,1)) as the reference compiles it (helper_math.h:1249-1252; tsdf.cu:31-33):
