@@ -337,9 +337,24 @@ def raycast_record(vol, K, dist_m, bins, torch, views=8, w=1280, h=960, replicat
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / views
     samples, hits = stats_vol.ray_stats()
+    # the reference's viewer loop itself (kernel.cpp:104: angle += 0.01 per view): consecutive views are nearly the same, which
+    # is what the marcher's longest-tile-first schedule (costs measured by the previous view) is built for
+    slow = [angles[1] + 0.01 * i for i in range(views + 2)]
+    for a in slow[:2]:
+        view(a)
+    torch.cuda.synchronize()
+    e0.record()
+    for a in slow[2:]:
+        view(a)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_slow = e0.elapsed_time(e1) / views
+    stats_vol.ray_stats()
     lit = int((out != np.iinfo(np.int64).max).sum().item()) if replicated is not None else int((out >= 0).sum().item())
     rec = {"ms_per_view": ms, "rays_per_s": w * h / (ms * 1e-3), "width": w, "height": h, "views": views,
-           "hit_fraction_last_view": lit / (w * h)}
+           "hit_fraction_last_view": lit / (w * h),
+           "orbit_step_0.01rad": {"ms_per_view": ms_slow, "rays_per_s": w * h / (ms_slow * 1e-3),
+                                  "what": str(views) + " consecutive views at the reference viewer's own increment (kernel.cpp:104) starting at angle %.2f rad" % angles[1]}}
     if replicated is None:
         peak, _ = measured_peaks()
         # samples x 8 taps x 4 B of SDF + hits x 8 taps x L bins (2 B each in the tiled 16-bit plane) + outputs

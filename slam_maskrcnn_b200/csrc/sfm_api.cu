@@ -127,6 +127,11 @@ struct sfm_volume {
 	size_t tile_bytes = 0;
 	unsigned long long *d_stats = nullptr;
 	unsigned long long *d_ray_stats = nullptr;  // [0] SDF samples gathered, [1] hits, cumulative (march_kernel)
+	unsigned *d_march_work = nullptr;           // march_kernel's tile counter and finished-warp counter (self-resetting)
+	unsigned *d_tile_cost = nullptr, *d_tile_order = nullptr;  // per 8x4-pixel tile: rounds of the last march; tiles by descending cost
+	size_t tile_cap = 0;
+	unsigned long long order_key = 0;           // image shape d_tile_order was built for (0: none)
+	int march_per_sm = 0;                       // resident march_kernel blocks per SM (occupancy, queried once)
 	uint64_t ray_samples_seen = 0, ray_hits_seen = 0;
 	uint32_t *d_err = nullptr;
 	size_t nbricks = 0;
@@ -553,6 +558,37 @@ int ray_blocks(int w, int h) {
 	return (int)((tiles + 3) / 4);  // 4 warps (128 threads) per block
 }
 
+// march_kernel on v->stream: a persistent grid (one resident wave) whose warps take the image's 8x4-pixel tiles
+// longest-first, by the costs the previous march of this handle measured for the same image shape; the order for the next
+// march is built right after this one (order_tiles_kernel, a few microseconds).
+int launch_march(sfm_volume *v, const RayVol &V, const RayCam &cam, float4 *d_hits, uint8_t *d_flags, int row0, int rows) {
+	const long long tiles = (long long)((cam.W + 7) / 8) * ((rows + 3) / 4);
+	if (tiles <= 0 || tiles > 0x7fffffffLL) return fail(SFM_ERR_INVALID, "image too large for the ray-marcher");
+	if ((size_t)tiles > v->tile_cap) {
+		cudaFree(v->d_tile_cost); cudaFree(v->d_tile_order);
+		v->d_tile_cost = v->d_tile_order = nullptr;
+		v->tile_cap = 0;
+		v->order_key = 0;
+		CU(cudaMalloc(&v->d_tile_cost, (size_t)tiles * 4));
+		CU(cudaMalloc(&v->d_tile_order, (size_t)tiles * 4));
+		v->tile_cap = (size_t)tiles;
+	}
+	if (!v->march_per_sm) {
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->march_per_sm, march_kernel, kMarchThreads, 0) != cudaSuccess || v->march_per_sm < 1)
+			v->march_per_sm = 1;
+	}
+	const int wpb = kMarchThreads / 32;
+	const int blocks = (int)std::max(1LL, std::min<long long>((tiles + wpb - 1) / wpb, (long long)v->march_per_sm * v->num_sms));
+	const unsigned long long key = ((unsigned long long)(unsigned)cam.W << 40) | ((unsigned long long)(unsigned)rows << 20) | (unsigned)row0 | (1ull << 63);
+	const unsigned *order = (v->order_key == key && !(v->desc.flags & SFM_FLAG_DEBUG_ABLATE && v->debug_ablate & 128)) ? v->d_tile_order : nullptr;
+	march_kernel<<<blocks, kMarchThreads, 0, v->stream>>>(V, cam, d_hits, d_flags, row0, rows, v->d_ray_stats, v->d_march_work, order, v->d_tile_cost);
+	LAUNCH_CHECK(v);
+	order_tiles_kernel<<<1, 1024, 0, v->stream>>>(v->d_tile_cost, (unsigned)tiles, v->d_tile_order);
+	LAUNCH_CHECK(v);
+	v->order_key = key;
+	return SFM_OK;
+}
+
 int require_full_volume(const sfm_volume *v, const char *what) {
 	if (v->g.z0 != 0 || v->g.nz != v->g.Dz)
 		return fail(SFM_ERR_INVALID, std::string(what) + ": this handle stores a z-slab; sharded ray-marching goes through sfm_raycast_keys_dev + a min-composite");
@@ -626,8 +662,8 @@ int enqueue_march_fold(sfm_volume *v, const float *E16, const uint8_t *d_mask) {
 	const int npix = v->W * v->H;
 	int rc = ensure_ray_buffers(v, (size_t)npix, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(V, cam, v->d_hits, nullptr, 0, v->H, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, V, cam, v->d_hits, nullptr, 0, v->H);
+	if (rc) return rc;
 	return launch_fold(v, v->d_fold, d_mask, nullptr, 1);
 }
 
@@ -1012,8 +1048,10 @@ int sfm_create(const sfm_desc *desc, sfm_volume **out) {
 	}
 	CU_OR_DESTROY(cudaMalloc(&v->d_stats, 2 * kStatSlots * 8));
 	CU_OR_DESTROY(cudaMemset(v->d_stats, 0, 2 * kStatSlots * 8));
-	CU_OR_DESTROY(cudaMalloc(&v->d_ray_stats, 16));
-	CU_OR_DESTROY(cudaMemset(v->d_ray_stats, 0, 16));
+	CU_OR_DESTROY(cudaMalloc(&v->d_ray_stats, 64));
+	CU_OR_DESTROY(cudaMemset(v->d_ray_stats, 0, 64));
+	CU_OR_DESTROY(cudaMalloc(&v->d_march_work, 8));
+	CU_OR_DESTROY(cudaMemset(v->d_march_work, 0, 8));
 	CU_OR_DESTROY(cudaMalloc(&v->d_err, 16));
 	{  // brick lists (k_integrate.cuh: WorkLists); ids pack x << 21 | brick row << 10 | z chunk
 		// brick shape on the 128-bit path: 32 planes per brick unless the slab is so thin that more than half the lanes
@@ -1099,6 +1137,7 @@ void sfm_destroy(sfm_volume *v) {
 	if (v->ev_call) cudaEventDestroy(v->ev_call);
 	cudaFree(v->d_stats);
 	cudaFree(v->d_ray_stats);
+	cudaFree(v->d_march_work); cudaFree(v->d_tile_cost); cudaFree(v->d_tile_order);
 #if SFM_K1_TMA_DEPTH
 	if (v->debug_ablate & 64) {
 		uint32_t e[4] = {0, 0, 0, 0};
@@ -1356,8 +1395,8 @@ int sfm_backproject(sfm_volume *v, const float *E16, float *probs, uint8_t *box_
 	if (rc) return rc;
 	CU(cudaMemsetAsync(v->d_probs, 0, npx * v->bins * 4, v->stream));  // tsdf.cu:428-429
 	CU(cudaMemsetAsync(v->d_box, 0, npx * v->bins, v->stream));
-	march_kernel<<<ray_blocks(v->W, v->H), 128, 0, v->stream>>>(make_ray_vol(v), make_backproj_cam(v, E16), v->d_hits, v->d_flags, 0, v->H, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, make_ray_vol(v), make_backproj_cam(v, E16), v->d_hits, v->d_flags, 0, v->H);
+	if (rc) return rc;
 	probs_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->desc.presence_thresh,
 		v->d_probs, v->d_box, v->d_t, v->d_flags);
 	LAUNCH_CHECK(v);
@@ -1377,8 +1416,8 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	if (rc) return rc;
 	rc = ensure_ray_buffers(v, (size_t)w * h, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr, 0, h, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr, 0, h);
+	if (rc) return rc;
 	shade_kernel<<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
 		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 0);
 	LAUNCH_CHECK(v);
@@ -1394,8 +1433,8 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	const size_t npx = (size_t)w * h;
 	rc = ensure_ray_buffers(v, npx, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h);
+	if (rc) return rc;
 	shade_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
 		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags, 0);
 	LAUNCH_CHECK(v);
@@ -1415,8 +1454,8 @@ int sfm_raycast_color(sfm_volume *v, const float *s2w16, const float *c3, int w,
 	const size_t npx = (size_t)w * h;
 	rc = ensure_ray_buffers(v, npx, false);
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, h), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h);
+	if (rc) return rc;
 	shade_color_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), v->planes.color, (int)npx, v->d_hits, v->d_bgr, v->d_t);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));
@@ -1593,9 +1632,9 @@ int sfm_raycast_band_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	CU(cudaSetDevice(v->desc.device));
 	int rc = require_full_volume(v, "sfm_raycast_band_dev");
 	if (rc) return rc;
-	march_kernel<<<ray_blocks(w, rows), 128, 0, v->stream>>>(make_ray_vol(v), make_show_cam(s2w16, c3, w, h), (float4 *)d_hits, nullptr,
-		row0, rows, v->d_ray_stats);
-	LAUNCH_CHECK(v);
+	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), (float4 *)d_hits, nullptr,
+		row0, rows);
+	if (rc) return rc;
 	return SFM_OK;
 }
 
