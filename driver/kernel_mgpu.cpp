@@ -146,7 +146,7 @@ int main(int argc, char **argv) {
 					const size_t cols = (size_t)dim * dim;
 					CUDA_OK(cudaMalloc(&q.d_sdf_mine, cols * per * 4));
 					CUDA_OK(cudaMalloc(&q.d_sdf_all, cols * per * 4 * ngpu));
-					CUDA_OK(cudaMalloc(&q.d_hits, (size_t)ngpu * ((H + ngpu - 1) / ngpu) * W * 16));
+					CUDA_OK(cudaMalloc(&q.d_hits, (size_t)ngpu * sfm_part_rows(H, ngpu) * W * 16));
 				}
 				SFM_OK_(sfm_mat4_inv(extrinsic, init_inv));  // tsdf.cu:177
 				mean_depth0 = mean;
@@ -223,7 +223,9 @@ int main(int argc, char **argv) {
 			for (auto &o : R) SFM_OK_(sfm_sdf_planes_dev(q.replica, o.own_z0, o.own_nz, q.d_sdf_all + (size_t)o.dev * cols * per, 0));
 			SFM_OK_(sfm_rebuild_skip_map(q.replica));
 		}
-		const int rows = (H + ngpu - 1) / ngpu;
+		// the image is split over the GPUs by interleaved 4-row tile rows (GPU p marches tile rows p, p + ngpu, ...): every GPU
+		// gets the same mix of cheap and expensive rows; each writes its share densely at its offset of d_hits
+		const size_t part_floats = (size_t)sfm_part_rows(H, ngpu) * W * 4;
 		vector<uint8_t> bgr(npx * 3);
 		float angle = 0.f;
 		for (int v = 0; v < views; v++) {
@@ -233,17 +235,15 @@ int main(int argc, char **argv) {
 			NCCL_OK(ncclGroupStart());
 			for (auto &q : R) {
 				CUDA_OK(cudaSetDevice(q.dev));
-				const int row0 = q.dev * rows, n = max(0, min(rows, H - row0));
-				CUDA_OK(cudaMemsetAsync(q.d_hits, 0, (size_t)ngpu * rows * W * 16, q.stream));
-				if (n > 0) SFM_OK_(sfm_raycast_band_dev(q.replica, s2w, c3, W, H, row0, n, q.d_hits));
-				// in-place all-gather: this GPU's band is already at its offset in d_hits
-				NCCL_OK(ncclAllGather(q.d_hits + (size_t)q.dev * rows * W * 4, q.d_hits, (size_t)rows * W * 4, ncclFloat, q.comm, q.stream));
+				SFM_OK_(sfm_raycast_part_dev(q.replica, s2w, c3, W, H, q.dev, ngpu, q.d_hits + (size_t)q.dev * part_floats));
+				// in-place all-gather: this GPU's share is already at its offset in d_hits
+				NCCL_OK(ncclAllGather(q.d_hits + (size_t)q.dev * part_floats, q.d_hits, part_floats, ncclFloat, q.comm, q.stream));
 			}
 			NCCL_OK(ncclGroupEnd());
 			NCCL_OK(ncclGroupStart());
 			for (auto &q : R) {
 				CUDA_OK(cudaSetDevice(q.dev));
-				SFM_OK_(sfm_label_hits_dev(q.vol, q.d_hits, W, H, q.d_keys));
+				SFM_OK_(sfm_label_hits_parts_dev(q.vol, q.d_hits, W, H, ngpu, q.d_keys));
 				NCCL_OK(ncclAllReduce(q.d_keys, q.d_keys, npx, ncclInt64, ncclMin, q.comm, q.stream));
 			}
 			NCCL_OK(ncclGroupEnd());

@@ -214,6 +214,16 @@ int sfm_sdf_planes_dev(sfm_volume *v, int z0, int n, void *d_buf, int to_buffer)
 int sfm_rebuild_skip_map(sfm_volume *v);
 int sfm_raycast_band_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, int row0, int rows, void *d_hits);
 int sfm_label_hits_dev(sfm_volume *v, const void *d_hits, int w, int h, void *d_keys);
+/* The same two steps with the image split over n_parts GPUs by INTERLEAVED 4-row tile rows (part p marches tile rows p,
+ * p + n_parts, ...): every part sees the same mix of cheap and expensive image regions, where contiguous bands differ by
+ * 3x (rays that graze the floor at the bottom of a view march ten times as many samples as rays into the sky).
+ *   sfm_raycast_part_dev       writes this part's hits densely into d_hits_part f32[sfm_part_rows(h, n_parts)][w][4]
+ *                              (zero where the image has ended) -- the chunk an all-gather collects from every rank
+ *   sfm_label_hits_parts_dev   like sfm_label_hits_dev on the all-gathered chunks (part-major); keys in raster order
+ * sfm_part_rows = 4 * ceil(ceil(h / 4) / n_parts). */
+int sfm_part_rows(int h, int n_parts);
+int sfm_raycast_part_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, int part, int n_parts, void *d_hits_part);
+int sfm_label_hits_parts_dev(sfm_volume *v, const void *d_hits_parts, int w, int h, int n_parts, void *d_keys);
 /* SDF samples gathered (8 taps x 4 bytes each) and surface hits of the ray marches since the previous call: the
  * algorithmic bytes of the ray kernels. */
 int sfm_ray_stats(sfm_volume *v, uint64_t *samples, uint64_t *hits);

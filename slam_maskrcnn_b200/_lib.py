@@ -98,6 +98,9 @@ SYMBOLS = {
     "sfm_rebuild_skip_map": (_i, [_vp]),
     "sfm_raycast_band_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sfm_label_hits_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sfm_part_rows": (_i, [_i, _i]),
+    "sfm_raycast_part_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sfm_label_hits_parts_dev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "sfm_ray_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfm_set_stream": (_i, [_vp, _vp]),
     "sfm_timer_start": (_i, [_vp]),

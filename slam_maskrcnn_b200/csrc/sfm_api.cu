@@ -561,7 +561,8 @@ int ray_blocks(int w, int h) {
 // march_kernel on v->stream: a persistent grid (one resident wave) whose warps take the image's 8x4-pixel tiles
 // longest-first, by the costs the previous march of this handle measured for the same image shape; the order for the next
 // march is built right after this one (order_tiles_kernel, a few microseconds).
-int launch_march(sfm_volume *v, const RayVol &V, const RayCam &cam, float4 *d_hits, uint8_t *d_flags, int row0, int rows) {
+int launch_march(sfm_volume *v, const RayVol &V, const RayCam &cam, float4 *d_hits, uint8_t *d_flags, int row0, int rows, int tstride = 1,
+	int compact = 0) {
 	const long long tiles = (long long)((cam.W + 7) / 8) * ((rows + 3) / 4);
 	if (tiles <= 0 || tiles > 0x7fffffffLL) return fail(SFM_ERR_INVALID, "image too large for the ray-marcher");
 	if ((size_t)tiles > v->tile_cap) {
@@ -579,9 +580,10 @@ int launch_march(sfm_volume *v, const RayVol &V, const RayCam &cam, float4 *d_hi
 	}
 	const int wpb = kMarchThreads / 32;
 	const int blocks = (int)std::max(1LL, std::min<long long>((tiles + wpb - 1) / wpb, (long long)v->march_per_sm * v->num_sms));
-	const unsigned long long key = ((unsigned long long)(unsigned)cam.W << 40) | ((unsigned long long)(unsigned)rows << 20) | (unsigned)row0 | (1ull << 63);
+	const unsigned long long key = ((unsigned long long)(unsigned)tstride << 52) | ((unsigned long long)(unsigned)cam.W << 36) | ((unsigned long long)(unsigned)rows << 18) |
+		(unsigned)row0 | (1ull << 63);
 	const unsigned *order = (v->order_key == key && !(v->desc.flags & SFM_FLAG_DEBUG_ABLATE && v->debug_ablate & 128)) ? v->d_tile_order : nullptr;
-	march_kernel<<<blocks, kMarchThreads, 0, v->stream>>>(V, cam, d_hits, d_flags, row0, rows, v->d_ray_stats, v->d_march_work, order, v->d_tile_cost);
+	march_kernel<<<blocks, kMarchThreads, 0, v->stream>>>(V, cam, d_hits, d_flags, row0, rows, tstride, compact, v->d_ray_stats, v->d_march_work, order, v->d_tile_cost);
 	LAUNCH_CHECK(v);
 	order_tiles_kernel<<<1, 1024, 0, v->stream>>>(v->d_tile_cost, (unsigned)tiles, v->d_tile_order);
 	LAUNCH_CHECK(v);
@@ -1419,7 +1421,7 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr, 0, h);
 	if (rc) return rc;
 	shade_kernel<<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
-		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 0);
+		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 0, 0, 0, 0);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
 }
@@ -1436,7 +1438,7 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h);
 	if (rc) return rc;
 	shade_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
-		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags, 0);
+		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags, 0, 0, 0, 0);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));  // viewer.cu:167
 	if (t_opt) CU(cudaMemcpyAsync(t_opt, v->d_t, npx * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -1638,15 +1640,32 @@ int sfm_raycast_band_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	return SFM_OK;
 }
 
-int sfm_label_hits_dev(sfm_volume *v, const void *d_hits, int w, int h, void *d_keys) {
-	if (!v || !d_hits || !d_keys || w <= 0 || h <= 0) return fail(SFM_ERR_INVALID, "bad argument");
+int sfm_part_rows(int h, int n_parts) { return (h > 0 && n_parts > 0) ? 4 * (((h + 3) / 4 + n_parts - 1) / n_parts) : 0; }
+
+int sfm_label_hits_parts_dev(sfm_volume *v, const void *d_hits, int w, int h, int n_parts, void *d_keys) {
+	if (!v || !d_hits || !d_keys || w <= 0 || h <= 0 || n_parts < 0) return fail(SFM_ERR_INVALID, "bad argument");
 	if (v->bins <= 0) return fail(SFM_ERR_INVALID, "labels are off (bins == 0)");
 	CU(cudaSetDevice(v->desc.device));
 	const int npx = w * h;
+	const int part_tile_rows = n_parts > 0 ? ((h + 3) / 4 + n_parts - 1) / n_parts : 0;
 	shade_kernel<<<(npx + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), npx, (const float4 *)d_hits, v->d_palette,
-		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1);
+		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1, w, n_parts, part_tile_rows);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
+}
+
+int sfm_label_hits_dev(sfm_volume *v, const void *d_hits, int w, int h, void *d_keys) {
+	return sfm_label_hits_parts_dev(v, d_hits, w, h, 0, d_keys);
+}
+
+int sfm_raycast_part_dev(sfm_volume *v, const float *s2w16, const float *c3, int w, int h, int part, int n_parts, void *d_hits_part) {
+	if (!v || !s2w16 || !c3 || !d_hits_part || w <= 0 || h <= 0 || n_parts <= 0 || part < 0 || part >= n_parts) return fail(SFM_ERR_INVALID, "bad argument");
+	if (!v->init) return fail(SFM_ERR_INVALID, "volume bounds not set");
+	CU(cudaSetDevice(v->desc.device));
+	int rc = require_full_volume(v, "sfm_raycast_part_dev");
+	if (rc) return rc;
+	const int part_tile_rows = ((h + 3) / 4 + n_parts - 1) / n_parts;
+	return launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), (float4 *)d_hits_part, nullptr, part * 4, part_tile_rows * 4, n_parts, 1);
 }
 
 int sfm_ray_stats(sfm_volume *v, uint64_t *samples, uint64_t *hits) {

@@ -315,25 +315,28 @@ class SlabVolume:
         return self.replica
 
     def raycast_replicated(self, s2w, c, w, h, group=None):
-        """One view on the replicated SDF: this rank marches its band of image rows (the single-volume march: same
-        kernel, same SDF bits), the hit positions are all-gathered (16 bytes per ray), every rank labels the hits
-        that fall into the planes it owns, and one MIN all-reduce composites the keys.  Two collectives per view,
-        no ray is marched twice.  Returns the composited int64 key image (identical on every rank)."""
+        """One view on the replicated SDF: this rank marches its share of the image -- every world-th 4-row tile row, so
+        that all ranks see the same mix of cheap and expensive regions (the single-volume march: same kernel, same SDF
+        bits) --, the hit positions are all-gathered (16 bytes per ray), every rank labels the hits that fall into the
+        planes it owns, and one MIN all-reduce composites the keys.  Two collectives per view, no ray is marched twice.
+        Returns the composited int64 key image (identical on every rank)."""
         import torch
         import torch.distributed as dist
         dev = torch.device("cuda", self.vol.desc.device)
-        rows = (h + self.world - 1) // self.world          # band height (the last band may be shorter)
-        hits = torch.zeros(self.world * rows * w * 4, dtype=torch.float32, device=dev)
-        row0 = self.rank * rows
-        nrows = max(0, min(rows, h - row0))
-        band = hits[row0 * w * 4:(row0 + rows) * w * 4]
-        if nrows > 0:
-            # the band kernel writes at image coordinates, so hand it a pointer shifted back to row 0 of the image
-            self.replica.raycast_band_dev(s2w, c, w, h, row0, nrows, hits.data_ptr())
-        if self.world > 1 and dist.is_initialized():
-            dist.all_gather_into_tensor(hits, band.clone(), group=group)
+        prow = self.replica.part_rows(h, self.world)
+        key = (w, h)
+        if getattr(self, "_ray_buf_key", None) != key:
+            self._ray_hits = torch.empty(self.world * prow * w * 4, dtype=torch.float32, device=dev)
+            self._ray_part = torch.empty(prow * w * 4, dtype=torch.float32, device=dev)
+            self._ray_buf_key = key
+        hits, part = self._ray_hits, self._ray_part
+        multi = self.world > 1 and dist.is_initialized()
+        mine = part if multi else hits
+        self.replica.raycast_part_dev(s2w, c, w, h, self.rank, self.world, mine.data_ptr())
+        if multi:
+            dist.all_gather_into_tensor(hits, part, group=group)
         keys = torch.empty(w * h, dtype=torch.int64, device=dev)
-        self.vol.label_hits_dev(hits.data_ptr(), w, h, keys.data_ptr())
+        self.vol.label_hits_parts_dev(hits.data_ptr(), w, h, self.world, keys.data_ptr())
         composite_keys(keys, group)
         return keys
 

@@ -306,6 +306,17 @@ class Volume:
     def label_hits_dev(self, d_hits, w, h, d_keys):
         check(self.lib.sfm_label_hits_dev(self._h, C.c_void_p(d_hits), w, h, C.c_void_p(d_keys)))
 
+    def raycast_part_dev(self, s2w, c, w, h, part, n_parts, d_hits_part):
+        """This part's share of the image (4-row tile rows part, part + n_parts, ...) marched into a dense buffer of
+        part_rows(h, n_parts) x w hits."""
+        check(self.lib.sfm_raycast_part_dev(self._h, _ptr(_f32(s2w, 16)), _ptr(_f32(c, 3)), w, h, int(part), int(n_parts), C.c_void_p(d_hits_part)))
+
+    def label_hits_parts_dev(self, d_hits_parts, w, h, n_parts, d_keys):
+        check(self.lib.sfm_label_hits_parts_dev(self._h, C.c_void_p(d_hits_parts), w, h, int(n_parts), C.c_void_p(d_keys)))
+
+    def part_rows(self, h, n_parts):
+        return int(self.lib.sfm_part_rows(int(h), int(n_parts)))
+
     def ray_stats(self):
         a, b = C.c_uint64(), C.c_uint64()
         check(self.lib.sfm_ray_stats(self._h, C.byref(a), C.byref(b)))

@@ -56,15 +56,15 @@ def test_full_size_80_bins_merge_and_raycast_whole_vs_slabs():
         del buf
     assert torch.equal(device_plane(rep, "sdf").view(torch.int32), device_plane(full, "sdf").view(torch.int32))
     rep.rebuild_skip_map()
-    rows = h // world
-    hits = torch.zeros(w * h * 4, dtype=torch.float32, device="cuda")
+    prow = rep.part_rows(h, world)
+    hits = torch.zeros(world * prow * w * 4, dtype=torch.float32, device="cuda")
     for r in range(world):
-        rep.raycast_band_dev(s2w, c, w, h, r * rows, rows, hits.data_ptr())
+        rep.raycast_part_dev(s2w, c, w, h, r, world, hits[r * prow * w * 4:].data_ptr())
     rep.synchronize()
     keys = None
     for v, *_ in slabs:
         k = torch.empty(w * h, dtype=torch.int64, device="cuda")
-        v.label_hits_dev(hits.data_ptr(), w, h, k.data_ptr())
+        v.label_hits_parts_dev(hits.data_ptr(), w, h, world, k.data_ptr())
         v.synchronize()
         keys = k if keys is None else torch.minimum(keys, k)
     same = keys == ref

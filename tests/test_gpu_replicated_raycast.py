@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("world,dims,bins,angle,wh", [(2, (64, 64, 64), 16, 0.2, None), (4, (64, 64, 96), 80, 0.9, None),
-                                                     (3, (56, 48, 60), 16, 2.6, (200, 150))])
+                                                     (3, (56, 48, 60), 16, 2.6, (200, 150)), (4, (64, 64, 64), 16, 1.3, (161, 122))])
 def test_replicated_raycast_equals_single_volume(world, dims, bins, angle, wh):
     import torch
     from slam_maskrcnn_b200 import Volume, orbit_camera
@@ -68,6 +68,25 @@ def test_replicated_raycast_equals_single_volume(world, dims, bins, angle, wh):
     assert (owners[hit] == 1).all() and (owners[~hit] == 0).all(), "every hit is labelled by exactly one slab"
     st = rep.ray_stats()
     assert st[1] == int(hit.sum()) and st[0] > st[1]
+
+    # the same with the image split by interleaved 4-row tile rows (what SlabVolume.raycast_replicated and the C++ driver
+    # use: every rank gets the same mix of cheap and expensive rows); chunk r of `parts` is what rank r contributes to the
+    # all-gather
+    prow = rep.part_rows(h, world)
+    assert prow % 4 == 0 and prow * world >= h
+    parts = torch.full((world * prow * w * 4,), float("nan"), dtype=torch.float32, device="cuda")
+    for r in range(world):
+        rep.raycast_part_dev(s2w, c, w, h, r, world, parts[r * prow * w * 4:].data_ptr())
+    rep.synchronize()
+    assert not bool(torch.isnan(parts).any()), "every entry of a part buffer is written (zeros past the end of the image)"
+    keys2 = None
+    for v, *_ in slabs:
+        k = torch.empty(w * h, dtype=torch.int64, device="cuda")
+        v.label_hits_parts_dev(parts.data_ptr(), w, h, world, k.data_ptr())
+        v.synchronize()
+        keys2 = k if keys2 is None else torch.minimum(keys2, k)
+    same = keys2 == ref
+    assert same.all(), f"interleaved parts: {int((~same).sum())} of {w * h} rays differ from the single-volume ray-cast"
     for v, *_ in slabs:
         v.close()
     rep.close()
