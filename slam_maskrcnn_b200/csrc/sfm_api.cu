@@ -1420,7 +1420,7 @@ int sfm_raycast_keys_dev(sfm_volume *v, const float *s2w16, const float *c3, int
 	if (rc) return rc;
 	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, nullptr, 0, h);
 	if (rc) return rc;
-	shade_kernel<<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
+	shade_kernel<8><<<(w * h + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), w * h, v->d_hits, v->d_palette,
 		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 0, 0, 0, 0);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
@@ -1437,7 +1437,7 @@ int sfm_raycast(sfm_volume *v, const float *s2w16, const float *c3, int w, int h
 	if (rc) return rc;
 	rc = launch_march(v, make_ray_vol(v), make_show_cam(s2w16, c3, w, h), v->d_hits, v->d_flags, 0, h);
 	if (rc) return rc;
-	shade_kernel<<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
+	shade_kernel<8><<<(int)((npx + 127) / 128), 128, 0, v->stream>>>(make_ray_vol(v), (int)npx, v->d_hits, v->d_palette,
 		v->d_bgr, v->d_t, v->d_label, nullptr, v->d_flags, 0, 0, 0, 0);
 	LAUNCH_CHECK(v);
 	CU(cudaMemcpyAsync(bgr, v->d_bgr, npx * 3, cudaMemcpyDeviceToHost, v->stream));  // viewer.cu:167
@@ -1648,8 +1648,13 @@ int sfm_label_hits_parts_dev(sfm_volume *v, const void *d_hits, int w, int h, in
 	CU(cudaSetDevice(v->desc.device));
 	const int npx = w * h;
 	const int part_tile_rows = n_parts > 0 ? ((h + 3) / 4 + n_parts - 1) / n_parts : 0;
-	shade_kernel<<<(npx + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), npx, (const float4 *)d_hits, v->d_palette,
-		nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1, w, n_parts, part_tile_rows);
+	// a slab that owns less than a third of the planes labels few, clustered hits: 32 lanes per hit there (shade_kernel)
+	if (v->g.own_nz * 3 < v->g.Dz)
+		shade_kernel<32><<<(npx + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), npx, (const float4 *)d_hits, v->d_palette,
+			nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1, w, n_parts, part_tile_rows);
+	else
+		shade_kernel<8><<<(npx + 127) / 128, 128, 0, v->stream>>>(make_ray_vol(v), npx, (const float4 *)d_hits, v->d_palette,
+			nullptr, nullptr, nullptr, (unsigned long long *)d_keys, nullptr, 1, w, n_parts, part_tile_rows);
 	LAUNCH_CHECK(v);
 	return SFM_OK;
 }
