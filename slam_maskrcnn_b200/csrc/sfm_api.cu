@@ -128,7 +128,7 @@ struct sfm_volume {
 	unsigned long long *d_stats = nullptr;
 	unsigned long long *d_ray_stats = nullptr;  // [0] SDF samples gathered, [1] hits, cumulative (march_kernel)
 	unsigned *d_march_work = nullptr;           // march_kernel's tile counter and finished-warp counter (self-resetting)
-	unsigned *d_tile_cost = nullptr, *d_tile_order = nullptr;  // per 8x4-pixel tile: rounds of the last march; tiles by descending cost
+	unsigned *d_tile_cost = nullptr, *d_tile_order = nullptr;  // per 8x4-pixel tile: cost (time) in the last march; tiles by descending cost
 	size_t tile_cap = 0;
 	unsigned long long order_key = 0;           // image shape d_tile_order was built for (0: none)
 	int march_per_sm = 0;                       // resident march_kernel blocks per SM (occupancy, queried once)

@@ -7,7 +7,7 @@ def main():
     D = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     dims = (D, D, D)
     sc, K, Kinv, place, frames = bench.make_frames(12, dims, "tum")
-    v = Volume(dims=dims, bins=0, width=640, height=480, K=K, Kinv=Kinv)
+    v = Volume(dims=dims, bins=0, width=640, height=480, K=K, Kinv=Kinv, flags=int(os.environ.get("PROBE_FLAGS", "0")))
     v.set_bounds(*place)
     for fr in frames:
         v.integrate_raw(fr["depth"], fr["color"], fr["mask"], fr["extrinsic"])
