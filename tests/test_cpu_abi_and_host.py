@@ -215,3 +215,17 @@ int run(cv::Mat depth, cv::Mat color, cv::Mat mask, cv::Mat extrinsic, float mea
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-I", os.path.join(ROOT, "tests", "stubs"), str(src)],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_image_shares_of_the_multi_gpu_raycast():
+    """sfm_part_rows: rows of the dense buffer one of n GPUs fills when the image is split by interleaved 4-row tile rows
+    (host arithmetic only): whole tile rows, together at least the image, at most one tile row of padding per share."""
+    from slam_maskrcnn_b200 import _lib
+    lib = _lib.load()
+    assert lib.sfm_part_rows(960, 8) == 120 and lib.sfm_part_rows(960, 1) == 960
+    assert lib.sfm_part_rows(122, 4) == 32 and lib.sfm_part_rows(150, 3) == 52
+    assert lib.sfm_part_rows(0, 4) == 0 and lib.sfm_part_rows(480, 0) == 0
+    for h in (1, 4, 5, 121, 480, 961):
+        for n in (1, 2, 3, 5, 8):
+            r = lib.sfm_part_rows(h, n)
+            assert r % 4 == 0 and r * n >= h and r * n < h + 4 * n + 4

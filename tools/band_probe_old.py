@@ -1,3 +1,7 @@
+"""Band-only variant of tools/band_probe.py (sfm_raycast_band_dev on a bins = 0 volume of D^3 voxels, 1280x960 views, the
+whole image and the eight 1/8 bands): it only uses entry points that older builds of the library have, so that the same
+script can time an exported older tree (git archive <commit> into build/oldsrc, built there) next to the current one.
+PROBE_FLAGS: sfm_desc flags of the volume (32 = SFM_FLAG_DEBUG_ABLATE, then SFM_DEBUG_ABLATE=128 marches in raster order)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
