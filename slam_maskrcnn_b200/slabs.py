@@ -322,7 +322,7 @@ class SlabVolume:
         Returns the composited int64 key image (identical on every rank)."""
         import torch
         import torch.distributed as dist
-        dev = torch.device("cuda", self.vol.desc.device)
+        dev = getattr(self, "_host_device", None) or torch.device("cuda", self.vol.desc.device)  # (CPU stand-ins in the gloo test)
         prow = self.replica.part_rows(h, self.world)
         key = (w, h)
         if getattr(self, "_ray_buf_key", None) != key:

@@ -335,3 +335,85 @@ def test_gloo_world2_sharded_fuse_host_logic():
         assert p.exitcode == 0
     for r in res:
         assert r[1], f"rank {r[0]}: {r[2]}"
+
+
+def _replicated_raycast_worker(rank, world, port, q):
+    """SlabVolume.raycast_replicated over gloo with stand-in volumes (no GPU): every rank marches ITS share of the image
+    (4-row tile rows rank, rank + world, ... written densely), the shares are all-gathered part-major, the labelling step
+    must find every pixel of the image at the documented place of the gathered buffer, and one MIN all-reduce must give
+    every rank the same composite."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from slam_maskrcnn_b200 import slabs
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H = 12, 10   # 3 tile rows for 2 ranks: the second share ends with a padding tile row
+        no_hit = np.iinfo(np.int64).max
+
+        def view(ptr, count, dtype):
+            size = np.dtype(dtype).itemsize
+            return np.frombuffer((ctypes.c_char * (count * size)).from_address(ptr), dtype=dtype)
+
+        def part_rows(h, n):
+            return 4 * (((h + 3) // 4 + n - 1) // n)
+
+        class FakeReplica:
+            def part_rows(self, h, n):
+                return part_rows(h, n)
+
+            def raycast_part_dev(self, s2w, c, w, h, part, n_parts, ptr):
+                prow = part_rows(h, n_parts)
+                buf = view(ptr, prow * w * 4, np.float32).reshape(prow, w, 4)
+                buf[:] = 0
+                for lr in range(prow // 4):
+                    for k in range(4):
+                        y = (part + lr * n_parts) * 4 + k
+                        if y < h:
+                            for x in range(w):
+                                buf[lr * 4 + k, x] = (x, y, 0, 1 + y * w + x)
+
+        class FakeSlab:
+            class desc:
+                device = 0
+
+            def label_hits_parts_dev(self, ptr, w, h, n_parts, keys_ptr):
+                prow = part_rows(h, n_parts)
+                hits = view(ptr, n_parts * prow * w * 4, np.float32).reshape(n_parts, prow, w, 4)
+                keys = view(keys_ptr, w * h, np.int64).reshape(h, w)
+                for y in range(h):
+                    gr = y // 4
+                    for x in range(w):
+                        e = hits[gr % n_parts, (gr // n_parts) * 4 + y % 4, x]
+                        assert tuple(e) == (x, y, 0, 1 + y * w + x), f"pixel ({x},{y}) not where the share layout puts it: {e}"
+                        owned = (x + y) % world == rank
+                        keys[y, x] = (int(np.float32(e[3]).view(np.uint32)) << 32 | (rank + 1)) if owned else no_hit
+
+        sv = slabs.SlabVolume.__new__(slabs.SlabVolume)
+        sv.rank, sv.world, sv.vol, sv.replica, sv.width, sv.height = rank, world, FakeSlab(), FakeReplica(), W, H
+        sv._host_device = torch.device("cpu")
+        keys = sv.raycast_replicated(np.eye(4, dtype=np.float32), np.zeros(3, np.float32), W, H).numpy().reshape(H, W)
+        yy, xx = np.mgrid[0:H, 0:W]
+        t = (1 + yy * W + xx).astype(np.float32)
+        want = (t.view(np.uint32).astype(np.int64) << 32) | ((xx + yy) % world + 1)
+        q.put((rank, bool((keys == want).all()), int((keys != want).sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_replicated_raycast_host_logic():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_replicated_raycast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1], f"rank {r[0]}: {r[2]} pixels of the composite differ"
