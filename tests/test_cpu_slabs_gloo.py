@@ -417,3 +417,43 @@ def test_gloo_world2_replicated_raycast_host_logic():
         assert p.exitcode == 0
     for r in res:
         assert r[1], f"rank {r[0]}: {r[2]} pixels of the composite differ"
+
+
+def test_slab_planner_properties_on_random_profiles():
+    """plan_slabs on random per-plane cost profiles (spiky ones included): the slabs tile [0, dz) in order, every slab is a
+    non-empty multiple of `align` planes no thicker than max_factor * dz / world, and the plan is never worse than equal
+    thickness by the planner's own cost model (owned planes + the charged share of the high-side halo)."""
+    from hypothesis import given, settings, strategies as st
+    from slam_maskrcnn_b200 import slabs
+
+    def plan_cost(plan, prof, align, halo_hi):
+        c = np.asarray(prof, np.float64)
+        c = c / c.sum()
+        worst = 0.0
+        for z0, n in plan:
+            own = c[z0:z0 + n].sum()
+            nxt = c[z0 + n:z0 + n + align].sum() * min(1.0, halo_hi / float(align))
+            worst = max(worst, own + nxt)
+        return worst
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(2, 8), st.integers(0, 2 ** 31 - 1), st.sampled_from([0, 4, 8]), st.sampled_from(["flat", "wall", "ramp", "noise"]))
+    def check(world, seed, halo_hi, shape):
+        align, dz = 8, 8 * 8 * world
+        rng = np.random.default_rng(seed)
+        prof = {"flat": np.ones(dz), "ramp": np.linspace(3.0, 0.05, dz), "noise": rng.random(dz) + 0.01,
+                "wall": np.full(dz, 0.02)}[shape].copy()
+        if shape == "wall":
+            w0 = int(rng.integers(0, dz - 16))
+            prof[w0:w0 + 12] += 5.0   # a fronto-parallel wall: a few very expensive planes
+        plan = slabs.plan_slabs(dz, world, prof, align=align, halo_hi=halo_hi)
+        assert len(plan) == world and plan[0][0] == 0
+        z = 0
+        for z0, n in plan:
+            assert z0 == z and n > 0 and n % align == 0 and n <= int(3.0 * dz / world)
+            z += n
+        assert z == dz
+        equal = [(r * (dz // world), dz // world) for r in range(world)]
+        assert plan_cost(plan, prof, align, halo_hi) <= plan_cost(equal, prof, align, halo_hi) + 1e-9
+
+    check()
