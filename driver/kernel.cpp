@@ -8,8 +8,9 @@
 //     waitKey are dropped, the last rendered view is written as a binary PPM instead;
 //   * paths, time window, frame cap, volume size and bin count are command-line arguments whose
 //     defaults are the reference's hard-coded values (kernel.cpp:39-44,60-61,74; tsdf.cuh:4,52);
-//   * the depth <-> mask association (kernel.cpp:64-74) is done up front and the three PNGs of frame i+1, i+2 are
-//     decoded by a second thread while frame i is fused (the reference decodes synchronously inside the loop);
+//   * the depth <-> mask association (kernel.cpp:64-74) is done up front and the three PNGs of the next frames are
+//     decoded by a pool of threads (--decode-threads, default 4) while frame i is fused, delivered in order (the
+//     reference decodes synchronously inside the loop);
 //     the volume is created from the first decoded frame's size, like the reference (tsdf.cu:225), and a frame of
 //     another size is an error instead of an out-of-bounds read.
 #include <algorithm>
@@ -35,7 +36,7 @@
 int main(int argc, char **argv) {
 	string root = ".", render = "render.ppm", render_color, ply;
 	double begin = 68164, end = 68170;  // kernel.cpp:60-61
-	int max_frames = 100, dim = 256, bins = MAX_OBJECTS, views = 10;
+	int max_frames = 100, dim = 256, bins = MAX_OBJECTS, views = 10, decode_threads = 4;
 	bool interp = false;  // --interp: lerp + slerp poses (TSDF_Python front-end) instead of the next entry
 	float intr[4] = {520.9f, 521.0f, 325.1f, 249.7f};  // kernel.cpp:39
 	for (int i = 1; i < argc; i++) {
@@ -47,6 +48,7 @@ int main(int argc, char **argv) {
 		else if (a == "--end") end = atof(next().c_str());
 		else if (a == "--max-frames") max_frames = atoi(next().c_str());
 		else if (a == "--views") views = atoi(next().c_str());
+		else if (a == "--decode-threads") decode_threads = std::max(1, atoi(next().c_str()));
 		else if (a == "--render") render = next();
 		else if (a == "--interp") interp = true;
 		else if (a == "--render-color") render_color = next();
@@ -75,20 +77,24 @@ int main(int argc, char **argv) {
 			if ((int)pairs.size() >= max_frames) break;            // kernel.cpp:73-74
 			pairs.push_back(make_pair(i, j));
 		}
-		// decode thread: keeps up to kAhead decoded frames ready
+		// decode pool: `decode_threads` threads keep up to kAhead decoded frames ready, in order (one frame is three PNGs,
+		// ~25 ms of inflate + unfilter on one core, against ~1 ms of GPU work: one thread feeds ~40 frames/s)
 		struct Decoded { sfm::Mat depth, mask, rgb; bool ok = false; };
-		const size_t kAhead = 3;
+		const size_t kAhead = std::max<size_t>(3, 2 * (size_t)decode_threads);
 		vector<Decoded> ring(kAhead);
+		vector<size_t> tag(kAhead, 0);  // tag[s] == k + 1: slot s holds frame k
 		mutex mu;
 		condition_variable cv_full, cv_free;
-		size_t produced = 0, consumed = 0;
+		size_t next = 0, consumed = 0;
 		bool stop = false;
-		thread decoder([&]() {
-			for (size_t k = 0; k < pairs.size(); k++) {
+		auto worker = [&]() {
+			for (;;) {
+				size_t k;
 				{
 					unique_lock<mutex> lk(mu);
-					cv_free.wait(lk, [&] { return stop || produced - consumed < kAhead; });
-					if (stop) return;
+					cv_free.wait(lk, [&] { return stop || next >= pairs.size() || next < consumed + kAhead; });
+					if (stop || next >= pairs.size()) return;
+					k = next++;  // slot k % kAhead is free: frame k - kAhead was consumed (next < consumed + kAhead)
 				}
 				Decoded d;
 				d.ok = read_png(depth_fn[pairs[k].first], d.depth, false) && read_png(mask_fn[pairs[k].second], d.mask, false) &&
@@ -96,25 +102,31 @@ int main(int argc, char **argv) {
 				{
 					lock_guard<mutex> lk(mu);
 					ring[k % kAhead] = std::move(d);
-					produced++;
+					tag[k % kAhead] = k + 1;
 				}
-				cv_full.notify_one();
+				cv_full.notify_all();
 			}
-		});
-		struct Joiner { thread &t; mutex &m; bool &stop; condition_variable &cv; ~Joiner() { { lock_guard<mutex> lk(m); stop = true; } cv.notify_all(); if (t.joinable()) t.join(); } } joiner{decoder, mu, stop, cv_free};
+		};
+		vector<thread> decoders;
+		for (int t = 0; t < decode_threads; t++) decoders.emplace_back(worker);
+		struct Joiner {
+			vector<thread> &ts; mutex &m; bool &stop; condition_variable &cv;
+			~Joiner() { { lock_guard<mutex> lk(m); stop = true; } cv.notify_all(); for (auto &t : ts) if (t.joinable()) t.join(); }
+		} joiner{decoders, mu, stop, cv_free};
 		unique_ptr<Viewer> viewer;
 		int width = 0, height = 0;
 		const auto t_start = chrono::steady_clock::now();
+		auto t_first = t_start;
 		for (size_t k = 0; k < pairs.size(); k++) {
 			const size_t i = pairs[k].first, jj = pairs[k].second;
 			Decoded d;
 			{
 				unique_lock<mutex> lk(mu);
-				cv_full.wait(lk, [&] { return produced > k; });
+				cv_full.wait(lk, [&] { return tag[k % kAhead] == k + 1; });
 				d = std::move(ring[k % kAhead]);
 				consumed++;
 			}
-			cv_free.notify_one();
+			cv_free.notify_all();
 			sfm::Mat &depth_img = d.depth, &mask_img = d.mask, &rgb_img = d.rgb;
 			if (!d.ok) {
 				cerr << "cannot decode " << depth_fn[i] << " / " << mask_fn[jj] << " / " << rgb_fn[jj] << endl;
@@ -151,15 +163,21 @@ int main(int argc, char **argv) {
 			} else
 				sfm_parse_extrinsic(low->second.data(), extrinsic);  // kernel.cpp:98
 			tsdf->parse_frame(depth_img, rgb_img, mask_img, extrinsic, mean);  // kernel.cpp:99
+			if (k == 0) {  // the first frame pays for the context, the volume's allocation and its clearing
+				sfm_synchronize(tsdf->handle());
+				t_first = chrono::steady_clock::now();
+			}
 		}
 		if (!tsdf) {
 			cerr << "no frame inside the time window" << endl;
 			return 2;
 		}
 		sfm_synchronize(tsdf->handle());
-		const double secs = chrono::duration<double>(chrono::steady_clock::now() - t_start).count();
-		cout << "frames from disk: " << pairs.size() << " in " << secs << " s = " << (pairs.size() / max(secs, 1e-9))
-		     << " frames/s (PNG decode on a second thread, " << kAhead << " frames ahead)" << endl;
+		const auto t_end = chrono::steady_clock::now();
+		const double secs = chrono::duration<double>(t_end - t_start).count(), steady = chrono::duration<double>(t_end - t_first).count();
+		cout << "frames from disk: " << pairs.size() << " in " << secs << " s = " << (pairs.size() / max(secs, 1e-9)) << " frames/s";
+		if (pairs.size() > 1) cout << "; after the first frame (context, allocation): " << ((pairs.size() - 1) / max(steady, 1e-9)) << " frames/s";
+		cout << " (PNG decode on " << decode_threads << " threads, up to " << kAhead << " frames ahead)" << endl;
 		const sfm_info info = tsdf->info();
 		cout << "fused " << info.n_obs << " frames, num_objs " << info.num_objs << ", voxel " << info.voxel[0] << " m" << endl;
 		if (viewer) {  // kernel.cpp:101-107 spins forever; we render `views` steps and keep the last image
